@@ -1,0 +1,39 @@
+// api.cu -- bookkeeping half of the C ABI (include/maskflow_b200.h): version, thread-local error slot, launch counter.
+// The operator entry points live next to their kernels (corr_fwd.cu, corr_bwd.cu, warp_fwd.cu, warp_bwd.cu).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace mfn {
+
+static thread_local char g_err[512] = "";
+static thread_local const char* g_kernel = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void note_kernel(const char* name) { g_kernel = name; }
+
+int check_launch(const char* kernel_name) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, "%s: launch failed: %s", kernel_name, cudaGetErrorString(e));
+  g_kernel = kernel_name;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_err[0] = '\0';
+  return MFN_OK;
+}
+
+}  // namespace mfn
+
+extern "C" int mfn_version(void) { return MFN_VERSION; }
+extern "C" const char* mfn_last_error(void) { return mfn::g_err; }
+extern "C" const char* mfn_last_kernel(void) { return mfn::g_kernel; }
+extern "C" unsigned long long mfn_launch_count(void) { return mfn::g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,143 @@
+// corr_bwd.cu -- correlation backward (K2) for sm_100a.
+//
+// Serves mfn_correlation_backward: the gradient of F.Correlation (network/MaskFlownet.py:193-195, 440-441) that the
+// reference obtains implicitly from autograd.record() / loss.backward() (network/pipeline.py:97,112-113).
+//
+//   g1[n,c,p]  = 1/C * sum_d  go'[q(d)][p]      * f2[c][p+d]
+//   g2[n,c,p'] = 1/C * sum_d  go'[q(d)][p'-d]   * f1[c][p'-d]
+//              = 1/C * sum_e  T[e][p']          * f1[c][p'+e]      with e = -d,  T[e][p'] = go'[q(-e)][p'+e]
+// so both sides are the same stencil "sum_e G[e][p] * X[c][p+e]" and share one kernel; side B gathers its G tile
+// through the index map above while loading it.  go' = go * (out > 0 ? 1 : slope) fuses the LeakyReLU backward.
+// Gather form on both sides: no atomics, deterministic.
+#include "common.cuh"
+
+namespace mfn {
+namespace k2 {
+constexpr int TH = 4, TW = 32, CK = 8, NT = 256;
+}
+
+template <int MD, bool SIDE_B>
+__global__ void __launch_bounds__(k2::NT)
+    corr_bwd_kernel(const float* __restrict__ go, const float* __restrict__ fwd_out, const float* __restrict__ X,
+                    float* __restrict__ gX, int N, int C, int H, int W, long long obs, float slope) {
+  using namespace k2;
+  constexpr int G = 2 * MD + 1, D = G * G;
+  constexpr int HR = TH + 2 * MD, HWD = TW + 8;
+  extern __shared__ __align__(16) float smem[];
+  float* Gt = smem;                  // [D][TH][TW]
+  float* Xs = smem + D * TH * TW;    // [CK][HR][HWD]
+
+  const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
+  const int tile = blockIdx.x;
+  const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+  const int x0 = tx * TW, y0 = ty * TH;
+  const int tid = threadIdx.x;
+  const size_t plane = (size_t)H * W;
+
+  const float* gon = go + (size_t)n * obs;
+  const float* fon = fwd_out ? fwd_out + (size_t)n * obs : nullptr;
+  for (int e = tid; e < D * TH * TW; e += NT) {
+    const int xx = e % TW, rr = (e / TW) % TH, q = e / (TW * TH);
+    const int ey = q / G - MD, ex = q % G - MD;
+    int ys = y0 + rr, xsrc = x0 + xx, qs = q;
+    bool ok = ys < H && xsrc < W;
+    if (SIDE_B) {
+      qs = (MD - ey) * G + (MD - ex);
+      ys += ey;
+      xsrc += ex;
+      ok = ok && ys >= 0 && ys < H && xsrc >= 0 && xsrc < W;
+    }
+    float v = 0.f;
+    if (ok) {
+      const size_t i = (size_t)qs * plane + (size_t)ys * W + xsrc;
+      v = __ldg(gon + i);
+      if (fon && !(__ldg(fon + i) > 0.f)) v *= slope;
+    }
+    Gt[e] = v;
+  }
+
+  const int qx = tid & 7, r = (tid >> 3) & 3, cc = tid >> 5;  // 8 quads x 4 rows x 8 channels
+  const float* Xn = X + (size_t)n * C * plane;
+  const float inv = 1.f / (float)C;
+  for (int c0 = 0; c0 < C; c0 += CK) {
+    __syncthreads();
+    for (int e = tid; e < CK * HR * HWD; e += NT) {
+      const int xx = e % HWD, yy = (e / HWD) % HR, c = c0 + e / (HWD * HR);
+      const int y = y0 - MD + yy, x = x0 - 4 + xx;
+      Xs[e] = (c < C && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(Xn + (size_t)c * plane + (size_t)y * W + x) : 0.f;
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int eyi = 0; eyi < G; ++eyi) {
+      const float* row = Xs + (cc * HR + r + eyi) * HWD + 4 * qx;
+      const float4 v0 = *reinterpret_cast<const float4*>(row);
+      const float4 v1 = *reinterpret_cast<const float4*>(row + 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(row + 8);
+      const float f[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+      for (int exi = 0; exi < G; ++exi) {
+        const float4 g4 = *reinterpret_cast<const float4*>(Gt + ((eyi * G + exi) * TH + r) * TW + 4 * qx);
+        acc[0] = fmaf(g4.x, f[0 + exi + (4 - MD)], acc[0]);
+        acc[1] = fmaf(g4.y, f[1 + exi + (4 - MD)], acc[1]);
+        acc[2] = fmaf(g4.z, f[2 + exi + (4 - MD)], acc[2]);
+        acc[3] = fmaf(g4.w, f[3 + exi + (4 - MD)], acc[3]);
+      }
+    }
+    const int c = c0 + cc, y = y0 + r, xb = x0 + 4 * qx;
+    if (c < C && y < H) {
+      float* o = gX + ((size_t)n * C + c) * plane + (size_t)y * W + xb;
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (xb + p < W) o[p] = acc[p] * inv;
+    }
+  }
+}
+
+template <int MD>
+static int launch_corr_bwd(const float* go, const float* fo, const float* d1, const float* d2, float* g1, float* g2,
+                           int N, int C, int H, int W, long long obs, float slope, cudaStream_t st) {
+  using namespace k2;
+  constexpr int G = 2 * MD + 1, D = G * G;
+  const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
+  const unsigned tiles = (unsigned)((long long)N * tilesX * tilesY);
+  const int smem = (int)sizeof(float) * (D * TH * TW + CK * (TH + 2 * MD) * (TW + 8));
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(corr_bwd_kernel<MD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(corr_bwd_kernel<MD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    done = true;
+  }
+  if (g1) {
+    corr_bwd_kernel<MD, false><<<tiles, NT, smem, st>>>(go, fo, d2, g1, N, C, H, W, obs, slope);
+    const int rc = check_launch("corr_bwd_kernel<sideA>");
+    if (rc) return rc;
+  }
+  if (g2) {
+    corr_bwd_kernel<MD, true><<<tiles, NT, smem, st>>>(go, fo, d1, g2, N, C, H, W, obs, slope);
+    return check_launch("corr_bwd_kernel<sideB>");
+  }
+  return MFN_OK;
+}
+
+}  // namespace mfn
+
+extern "C" int mfn_correlation_backward(const float* grad_out, const float* out, const float* data1,
+                                        const float* data2, float* grad1, float* grad2, int N, int C, int H, int W,
+                                        int max_displacement, long long out_batch_stride, float leaky_slope,
+                                        void* stream) {
+  using namespace mfn;
+  MFN_REQUIRE(grad_out && data1 && data2 && (grad1 || grad2), MFN_ERR_INVALID_ARG,
+              "mfn_correlation_backward: null pointer");
+  MFN_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, MFN_ERR_INVALID_ARG, "mfn_correlation_backward: non-positive extent");
+  MFN_REQUIRE(max_displacement == 4 || max_displacement == 2, MFN_ERR_UNSUPPORTED,
+              "mfn_correlation_backward: max_displacement must be 4 or 2 (the reference's values), got %d",
+              max_displacement);
+  const int G = 2 * max_displacement + 1;
+  const long long obs = out_batch_stride ? out_batch_stride : (long long)G * G * H * W;
+  MFN_REQUIRE(obs >= (long long)G * G * H * W, MFN_ERR_INVALID_ARG, "mfn_correlation_backward: out_batch_stride too small");
+  cudaStream_t st = as_stream(stream);
+  return max_displacement == 4
+             ? launch_corr_bwd<4>(grad_out, out, data1, data2, grad1, grad2, N, C, H, W, obs, leaky_slope, st)
+             : launch_corr_bwd<2>(grad_out, out, data1, data2, grad1, grad2, N, C, H, W, obs, leaky_slope, st);
+}

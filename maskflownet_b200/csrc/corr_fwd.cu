@@ -1,0 +1,535 @@
+// corr_fwd.cu -- correlation cost-volume forward kernels (K1) for sm_100a.
+//
+// Serves mfn_correlation_forward (include/maskflow_b200.h), i.e. the reference's
+//   F.Correlation(im1, im2, pad_size=md, kernel_size=1, max_displacement=md, stride1=1, stride2=1,
+//                 is_multiply=1)        network/MaskFlownet.py:193-195 (md=4), :440-441 (md=2)
+// followed by LeakyReLU(0.1) (:217 ...), fused as the epilogue.
+//
+// Three kernels:
+//   corr_generic_kernel   every MXNet parameter combination, one thread per output element (exact fp32)
+//   corr_simt_kernel      tiled fp32-FMA kernel for the reference regime (exact fp32 accumulation)
+//   corr_mma_kernel       tensor-core kernel for the reference regime: operands split into bf16 hi/lo
+//                         halves, 3 MMAs per product (hi*hi + hi*lo + lo*hi), fp32 accumulation.
+//                         Warp-specialised: producer warps stream fp32 NCHW tiles from HBM/L2, split and
+//                         transpose them into channel-contiguous bf16 tiles in shared memory; consumer warps
+//                         run ldmatrix + mma.sync on a banded formulation (16 f2 positions x 8 pixels per
+//                         MMA, 9/16 of the issued MACs useful) and write the D planes with coalesced stores.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mfn {
+
+// =====================================================================================================
+// Generic kernel: literal MXNet semantics (zero padding handled by bounds tests instead of padded temps).
+// =====================================================================================================
+__global__ void corr_generic_kernel(const float* __restrict__ d1, const float* __restrict__ d2,
+                                    float* __restrict__ out, int N, int C, int H, int W, int pad,
+                                    int ks, int md, int s1, int s2, int is_mul, int D, int OH, int OW,
+                                    long long out_bs, float slope) {
+  const int G = 2 * (md / s2) + 1, r = md / s2;
+  const long long total = (long long)N * D * OH * OW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % OW);
+    const int i = (int)((idx / OW) % OH);
+    const int q = (int)((idx / ((long long)OW * OH)) % D);
+    const int n = (int)(idx / ((long long)OW * OH * D));
+    // coordinates in the UNPADDED inputs
+    const int x1 = j * s1 + md - pad, y1 = i * s1 + md - pad;
+    const int x2 = x1 + (q % G - r) * s2, y2 = y1 + (q / G - r) * s2;
+    float acc = 0.f;
+    for (int h = 0; h < ks; ++h)
+      for (int w = 0; w < ks; ++w) {
+        const int ya = y1 + h, xa = x1 + w, yb = y2 + h, xb = x2 + w;
+        // outside the zero-padded extent nothing is read at all (MXNet's temporaries end there)
+        if (ya < -pad || ya >= H + pad || xa < -pad || xa >= W + pad) continue;
+        const bool ina = (ya >= 0 && ya < H && xa >= 0 && xa < W);
+        const bool pb = (yb >= -pad && yb < H + pad && xb >= -pad && xb < W + pad);
+        const bool inb = (yb >= 0 && yb < H && xb >= 0 && xb < W);
+        if (is_mul) {
+          if (!(ina && inb)) continue;
+          const float* a = d1 + ((size_t)n * C * H + ya) * W + xa;
+          const float* b = d2 + ((size_t)n * C * H + yb) * W + xb;
+          for (int c = 0; c < C; ++c) acc += __ldg(a + (size_t)c * H * W) * __ldg(b + (size_t)c * H * W);
+        } else {
+          if (!pb) {  // d2 position beyond the padded temp: MXNet would read out of its buffer; we treat it as 0
+            if (ina) {
+              const float* a = d1 + ((size_t)n * C * H + ya) * W + xa;
+              for (int c = 0; c < C; ++c) acc += fabsf(__ldg(a + (size_t)c * H * W));
+            }
+            continue;
+          }
+          for (int c = 0; c < C; ++c) {
+            const float av = ina ? __ldg(d1 + (((size_t)n * C + c) * H + ya) * W + xa) : 0.f;
+            const float bv = inb ? __ldg(d2 + (((size_t)n * C + c) * H + yb) * W + xb) : 0.f;
+            acc += fabsf(av - bv);
+          }
+        }
+      }
+    const float v = acc / (float)(ks * ks * C);
+    out[(size_t)n * out_bs + ((size_t)q * OH + i) * OW + j] = leaky(v, slope);
+  }
+}
+
+// =====================================================================================================
+// SIMT tiled kernel (exact fp32).  CTA tile = 8 rows x 32 pixels; thread = (dy, row, 4-pixel strip), holding
+// 4 x G accumulators; channels staged in chunks of 16 through shared memory.
+// =====================================================================================================
+namespace simt {
+constexpr int TH = 8, TW = 32, CK = 16;
+}
+
+template <int MD>
+__global__ void __launch_bounds__(64 * (2 * MD + 1))
+    corr_simt_kernel(const float* __restrict__ d1, const float* __restrict__ d2, float* __restrict__ out,
+                     int N, int C, int H, int W, long long out_bs, float slope) {
+  using namespace simt;
+  constexpr int G = 2 * MD + 1;
+  constexpr int HR = TH + 2 * MD;
+  constexpr int HWD = TW + 8;  // f2 tile always carries a 4-pixel halo so that rows stay 16B aligned
+  constexpr int NT = 64 * G;
+  extern __shared__ __align__(16) float smem[];
+  float* s1 = smem;                  // [CK][TH][TW]
+  float* s2 = smem + CK * TH * TW;   // [CK][HR][HWD]
+
+  const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
+  const int tile = blockIdx.x;
+  const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+  const int x0 = tx * TW, y0 = ty * TH;
+  const int tid = threadIdx.x;
+  const int qx = tid & 7, r = (tid >> 3) & 7, dyi = tid >> 6;  // dyi in [0,G)
+
+  float acc[G][4];
+#pragma unroll
+  for (int a = 0; a < G; ++a)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[a][p] = 0.f;
+
+  const float* b1 = d1 + (size_t)n * C * H * W;
+  const float* b2 = d2 + (size_t)n * C * H * W;
+  for (int c0 = 0; c0 < C; c0 += CK) {
+    __syncthreads();
+    for (int e = tid; e < CK * TH * TW; e += NT) {
+      const int xx = e % TW, yy = (e / TW) % TH, cc = e / (TW * TH);
+      const int c = c0 + cc, y = y0 + yy, x = x0 + xx;
+      s1[e] = (c < C && y < H && x < W) ? __ldg(b1 + ((size_t)c * H + y) * W + x) : 0.f;
+    }
+    for (int e = tid; e < CK * HR * HWD; e += NT) {
+      const int xx = e % HWD, yy = (e / HWD) % HR, cc = e / (HWD * HR);
+      const int c = c0 + cc, y = y0 - MD + yy, x = x0 - 4 + xx;
+      s2[e] = (c < C && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(b2 + ((size_t)c * H + y) * W + x) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int cc = 0; cc < CK; ++cc) {
+      const float4 a = *reinterpret_cast<const float4*>(s1 + (cc * TH + r) * TW + 4 * qx);
+      const float* row = s2 + (cc * HR + r + dyi) * HWD + 4 * qx;  // element 0 == pixel x-4
+      const float4 v0 = *reinterpret_cast<const float4*>(row);
+      const float4 v1 = *reinterpret_cast<const float4*>(row + 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(row + 8);
+      const float f[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int dxi = 0; dxi < G; ++dxi)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[dxi][p] = fmaf(av[p], f[p + dxi + (4 - MD)], acc[dxi][p]);
+    }
+  }
+  const int y = y0 + r, xb = x0 + 4 * qx;
+  if (y >= H) return;
+  const float inv = 1.f / (float)C;
+  float* o = out + (size_t)n * out_bs + (size_t)y * W + xb;
+  const bool vec = ((W & 3) == 0) && ((out_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+  for (int dxi = 0; dxi < G; ++dxi) {
+    float* op = o + (size_t)(dyi * G + dxi) * H * W;
+    float v[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) v[p] = leaky(acc[dxi][p] * inv, slope);
+    if (vec && xb + 3 < W) {
+      *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (xb + p < W) op[p] = v[p];
+    }
+  }
+}
+
+// =====================================================================================================
+// Tensor-core kernel (bf16 hi/lo split, mma.sync.m16n8k16).
+// =====================================================================================================
+namespace tc {
+constexpr int TH = 6;    // tile rows
+constexpr int TW = 32;   // tile pixels per row
+constexpr int CK = 32;   // channels per pipeline stage
+constexpr int RS = 2 * CK + 16;  // bytes per pixel row of a bf16 tile (80: odd multiple of 16 -> conflict-free ldmatrix)
+constexpr int HX = 4;    // horizontal halo carried in shared memory (always 4 so that rows stay 16B aligned)
+constexpr int HWP = TW + 2 * HX;  // 40 pixels per halo row
+constexpr int NCONS = 12;         // consumer warps: (row 0..5) x (16-pixel half 0..1)
+constexpr int NPROD = 4;          // producer warps
+constexpr int NTHREADS = 32 * (NCONS + NPROD);
+constexpr int OCT_PER_ROW = (TW + 16) / 8;  // aligned 8-pixel groups spanning [x0-8, x0+TW+8)
+constexpr int STG_STRIDE = 20;    // floats per dx row of the per-warp output staging buffer
+
+__host__ __device__ constexpr int halo_rows(int md) { return TH + 2 * md; }
+__host__ __device__ constexpr int stage_bytes(int md) { return halo_rows(md) * HWP * RS * 2; }  // hi + lo
+__host__ __device__ constexpr int smem_bytes(int md) {
+  return 2 * stage_bytes(md) + NCONS * (2 * md + 1) * STG_STRIDE * 4 + 64;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// (a, b) fp32 -> packed bf16x2 "hi" (a in the low half) and the bf16x2 of the remainders "lo".
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+}  // namespace tc
+
+// VEC: rows are 16-byte aligned (W % 4 == 0 and 16B-aligned base) -> float4 producer loads.
+template <int MD, bool VEC>
+__global__ void __launch_bounds__(tc::NTHREADS, 1)
+    corr_mma_kernel(const float* __restrict__ d1, const float* __restrict__ d2, float* __restrict__ out,
+                    int N, int C, int H, int W, long long out_bs, float slope, int tilesX, int tilesY,
+                    int numTiles) {
+  using namespace tc;
+  constexpr int G = 2 * MD + 1;
+  constexpr int HR = halo_rows(MD);
+  constexpr int STAGE = stage_bytes(MD);
+  constexpr int LO_OFF = HR * HWP * RS;  // byte offset of the "lo" tile inside a stage
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* stage0 = smem_raw;
+  float* stg_all = reinterpret_cast<float*>(smem_raw + 2 * STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * STAGE + NCONS * G * STG_STRIDE * 4);
+  const uint32_t bar_full = smem_u32(bars);        // [2]
+  const uint32_t bar_empty = smem_u32(bars + 2);   // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, NPROD * 32);
+    mbar_init(bar_full + 8, NPROD * 32);
+    mbar_init(bar_empty, NCONS);
+    mbar_init(bar_empty + 8, NCONS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int nChunks = (C + CK - 1) / CK;
+  const size_t plane = (size_t)H * W;
+
+  if (warp >= NCONS) {
+    // ================================ PRODUCERS ================================
+    const int pw = warp - NCONS;
+    const int m = lane >> 4;   // which aligned quad of the octet
+    const int j = lane & 15;   // channel pair inside the chunk
+    uint32_t s = 0;
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+      const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+      const int x0 = tx * TW, y0 = ty * TH;
+      const float* base = d2 + (size_t)n * C * plane;
+      for (int ch = 0; ch < nChunks; ++ch, ++s) {
+        const uint32_t b = s & 1u, u = s >> 1;
+        mbar_wait(bar_empty + 8 * b, (u & 1u) ^ 1u);
+        unsigned char* st = stage0 + b * STAGE;
+        const int ca = ch * CK + 2 * j;
+        const bool c_ok0 = ca < C, c_ok1 = ca + 1 < C;
+        const float* pc = base + (size_t)ca * plane;
+        constexpr int NOR = HR * OCT_PER_ROW;  // octet-rows in this stage
+        constexpr int U = 3;
+        for (int o0 = pw; o0 < NOR; o0 += NPROD * U) {
+          float4 v0[U], v1[U];
+          int pxr[U], rr[U];
+#pragma unroll
+          for (int uu = 0; uu < U; ++uu) {
+            const int o = o0 + uu * NPROD;
+            v0[uu] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v1[uu] = v0[uu];
+            rr[uu] = o / OCT_PER_ROW;
+            const int oct = o - rr[uu] * OCT_PER_ROW;
+            pxr[uu] = 8 * oct + 4 * m - HX;  // pixel index inside the halo row; -4 and 40 are the masked quads
+            const int y = y0 - MD + rr[uu];
+            const int x = x0 - 8 + 8 * oct + 4 * m;
+            if (o < NOR && pxr[uu] >= 0 && pxr[uu] < HWP && y >= 0 && y < H) {
+              const float* p = pc + (size_t)y * W + x;
+              if (VEC) {
+                if (x >= 0 && x < W) {  // W % 4 == 0: the quad is entirely inside or outside
+                  if (c_ok0) v0[uu] = __ldg(reinterpret_cast<const float4*>(p));
+                  if (c_ok1) v1[uu] = __ldg(reinterpret_cast<const float4*>(p + plane));
+                }
+              } else {
+                float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (x + e >= 0 && x + e < W) {
+                    if (c_ok0) t0[e] = __ldg(p + e);
+                    if (c_ok1) t1[e] = __ldg(p + plane + e);
+                  }
+                v0[uu] = make_float4(t0[0], t0[1], t0[2], t0[3]);
+                v1[uu] = make_float4(t1[0], t1[1], t1[2], t1[3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int uu = 0; uu < U; ++uu) {
+            const int o = o0 + uu * NPROD;
+            if (o < NOR && pxr[uu] >= 0 && pxr[uu] < HWP) {
+              unsigned char* dst = st + (size_t)(rr[uu] * HWP + pxr[uu]) * RS + 4 * j;
+              const float a[4] = {v0[uu].x, v0[uu].y, v0[uu].z, v0[uu].w};
+              const float c[4] = {v1[uu].x, v1[uu].y, v1[uu].z, v1[uu].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                uint32_t hi, lo;
+                split_pair(a[e], c[e], hi, lo);
+                *reinterpret_cast<uint32_t*>(dst + e * RS) = hi;
+                *reinterpret_cast<uint32_t*>(dst + e * RS + LO_OFF) = lo;
+              }
+            }
+          }
+        }
+        mbar_arrive(bar_full + 8 * b);  // release: this thread's tile writes are visible to waiters
+      }
+    }
+  } else {
+    // ================================ CONSUMERS ================================
+    const int r = warp >> 1;            // tile row of this warp's item
+    const int xs = (warp & 1) * 16;     // first pixel (tile-relative) of the 16-pixel item
+    const int g = lane >> 2, j = lane & 3;
+    float* stg = stg_all + warp * (G * STG_STRIDE);
+    const float invC = 1.f / (float)C;
+
+    // per-lane ldmatrix byte offsets inside a stage (excluding the dy row and k-step terms)
+    const int l8 = lane & 7, mi = lane >> 3;
+    // loads 1/2: matrices (block mi&1, k-half mi>>1) of the hi / lo tile
+    const uint32_t off12 = (uint32_t)((xs + 8 * (mi & 1) + l8) * RS + 16 * (mi >> 1));
+    // load 3: matrices (hi|lo = mi>>1, block 2, k-half mi&1)
+    const uint32_t off3 = (uint32_t)((xs + 16 + l8) * RS + 16 * (mi & 1) + (mi >> 1) * LO_OFF);
+
+    uint32_t s = 0;
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+      const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+      const int x0 = tx * TW, y0 = ty * TH;
+      const int y = y0 + r;
+      const float* f1n = d1 + (size_t)n * C * plane;
+
+      float acc[G][2][4];
+#pragma unroll
+      for (int d = 0; d < G; ++d)
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[d][t][i] = 0.f;
+
+      for (int ch = 0; ch < nChunks; ++ch, ++s) {
+        const uint32_t b = s & 1u, u = s >> 1;
+        // ---- B fragments (data1) straight from global memory: lane (g, j) owns pixel g, channels 2j.. ----
+        uint32_t bh[2][2][2], bl[2][2][2];  // [k-step][tile][reg]
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int x = x0 + xs + 8 * t + g;
+            const int c = ch * CK + 16 * kk + 2 * j;
+            const bool ok = (y < H) && (x < W);
+            const float* p = f1n + (size_t)c * plane + (size_t)y * W + x;
+            const float e0 = (ok && c < C) ? __ldg(p) : 0.f;
+            const float e1 = (ok && c + 1 < C) ? __ldg(p + plane) : 0.f;
+            const float e8 = (ok && c + 8 < C) ? __ldg(p + 8 * plane) : 0.f;
+            const float e9 = (ok && c + 9 < C) ? __ldg(p + 9 * plane) : 0.f;
+            split_pair(e0, e1, bh[kk][t][0], bl[kk][t][0]);
+            split_pair(e8, e9, bh[kk][t][1], bl[kk][t][1]);
+          }
+        mbar_wait(bar_full + 8 * b, u & 1u);
+        const uint32_t st = smem_u32(stage0 + b * STAGE);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+          for (int d = 0; d < G; ++d) {
+            const uint32_t rowoff = (uint32_t)((r + d) * HWP * RS + 32 * kk);
+            uint32_t h[4], l[4], x3[4];
+            ldsm_x4(st + rowoff + off12, h);
+            ldsm_x4(st + rowoff + off12 + LO_OFF, l);
+            ldsm_x4(st + rowoff + off3, x3);
+            // tile 0: rows = blocks 0,1 ; tile 1: rows = blocks 1,2
+            mma_bf16(acc[d][0], h[0], h[1], h[2], h[3], bl[kk][0][0], bl[kk][0][1]);
+            mma_bf16(acc[d][0], l[0], l[1], l[2], l[3], bh[kk][0][0], bh[kk][0][1]);
+            mma_bf16(acc[d][0], h[0], h[1], h[2], h[3], bh[kk][0][0], bh[kk][0][1]);
+            mma_bf16(acc[d][1], h[1], x3[0], h[3], x3[1], bl[kk][1][0], bl[kk][1][1]);
+            mma_bf16(acc[d][1], l[1], x3[2], l[3], x3[3], bh[kk][1][0], bh[kk][1][1]);
+            mma_bf16(acc[d][1], h[1], x3[0], h[3], x3[1], bh[kk][1][0], bh[kk][1][1]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+      }
+
+      // ---- epilogue: accumulators -> per-warp staging -> coalesced plane rows ----
+      // accumulator (row, col) of tile t: f2 position xs+8t-4+row versus pixel xs+8t+col  =>  dx = row-col-4
+      float* obase = out + (size_t)n * out_bs + (size_t)y * W + (x0 + xs);
+      const int p = lane & 15, hsel = lane >> 4;
+#pragma unroll
+      for (int d = 0; d < G; ++d) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = g + 8 * (i >> 1), col = 2 * j + (i & 1);
+            const int dxi = row - col - 4 + MD;
+            if (dxi >= 0 && dxi < G) stg[dxi * STG_STRIDE + 8 * t + col] = leaky(acc[d][t][i] * invC, slope);
+          }
+        __syncwarp();
+        if (y < H && x0 + xs + p < W) {
+#pragma unroll
+          for (int dxi = hsel; dxi < G; dxi += 2)
+            obase[(size_t)(d * G + dxi) * plane + p] = stg[dxi * STG_STRIDE + p];
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// Host dispatch
+// =====================================================================================================
+static int launch_generic(const float* d1, const float* d2, float* out, int N, int C, int H, int W, int pad,
+                          int ks, int md, int s1, int s2, int mul, int D, int OH, int OW, long long obs,
+                          float slope, cudaStream_t st) {
+  const long long total = (long long)N * D * OH * OW;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  corr_generic_kernel<<<(unsigned)blocks, threads, 0, st>>>(d1, d2, out, N, C, H, W, pad, ks, md, s1, s2, mul,
+                                                           D, OH, OW, obs, slope);
+  return check_launch("corr_generic_kernel");
+}
+
+template <int MD>
+static int launch_simt(const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,
+                       float slope, cudaStream_t st) {
+  using namespace simt;
+  constexpr int G = 2 * MD + 1;
+  const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
+  const long long tiles = (long long)N * tilesX * tilesY;
+  const size_t smem = sizeof(float) * CK * (TH * TW + (TH + 2 * MD) * (TW + 8));
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(corr_simt_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  corr_simt_kernel<MD><<<(unsigned)tiles, 64 * G, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope);
+  return check_launch(MD == 4 ? "corr_simt_kernel<4>" : "corr_simt_kernel<2>");
+}
+
+template <int MD, bool VEC>
+static int launch_mma_impl(const float* d1, const float* d2, float* out, int N, int C, int H, int W,
+                           long long obs, float slope, cudaStream_t st) {
+  using namespace tc;
+  const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
+  const long long tiles = (long long)N * tilesX * tilesY;
+  const int smem = smem_bytes(MD);
+  static bool attr_done = false;  // per template instantiation; the attribute is per-function (all devices share the module)
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(corr_mma_kernel<MD, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_mma_kernel): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  corr_mma_kernel<MD, VEC><<<grid, NTHREADS, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope, tilesX, tilesY,
+                                                         (int)tiles);
+  return check_launch(MD == 4 ? (VEC ? "corr_mma_kernel<4,vec>" : "corr_mma_kernel<4,scalar>")
+                              : (VEC ? "corr_mma_kernel<2,vec>" : "corr_mma_kernel<2,scalar>"));
+}
+
+template <int MD>
+static int launch_mma(const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,
+                      float slope, cudaStream_t st) {
+  const bool vec = (W % 4 == 0) && aligned(d2, 16);
+  return vec ? launch_mma_impl<MD, true>(d1, d2, out, N, C, H, W, obs, slope, st)
+             : launch_mma_impl<MD, false>(d1, d2, out, N, C, H, W, obs, slope, st);
+}
+
+}  // namespace mfn
+
+extern "C" int mfn_correlation_forward(const float* data1, const float* data2, float* out, int N, int C, int H,
+                                       int W, int pad_size, int kernel_size, int max_displacement, int stride1,
+                                       int stride2, int is_multiply, long long out_batch_stride,
+                                       float leaky_slope, int algo, void* stream) {
+  using namespace mfn;
+  MFN_REQUIRE(data1 && data2 && out, MFN_ERR_INVALID_ARG, "mfn_correlation_forward: null pointer");
+  MFN_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, MFN_ERR_INVALID_ARG,
+              "mfn_correlation_forward: non-positive extent (N=%d C=%d H=%d W=%d)", N, C, H, W);
+  MFN_REQUIRE(kernel_size >= 1 && (kernel_size & 1), MFN_ERR_INVALID_ARG,
+              "mfn_correlation_forward: kernel_size must be odd (got %d)", kernel_size);
+  MFN_REQUIRE(stride1 >= 1 && stride2 >= 1 && max_displacement >= 0 && pad_size >= 0, MFN_ERR_INVALID_ARG,
+              "mfn_correlation_forward: bad stride/displacement/pad");
+  MFN_REQUIRE(aligned(data1, 4) && aligned(data2, 4) && aligned(out, 4), MFN_ERR_ALIGNMENT,
+              "mfn_correlation_forward: pointers must be 4-byte aligned");
+  const int kr = (kernel_size - 1) / 2, border = max_displacement + kr;
+  const int ph = H + 2 * pad_size, pw = W + 2 * pad_size;
+  const int OH = (ph - 2 * border + stride1 - 1) / stride1, OW = (pw - 2 * border + stride1 - 1) / stride1;
+  MFN_REQUIRE(ph - 2 * border >= 1 && pw - 2 * border >= 1, MFN_ERR_INVALID_ARG,
+              "mfn_correlation_forward: empty output");
+  const int r = max_displacement / stride2, G = 2 * r + 1, D = G * G;
+  const long long obs = out_batch_stride ? out_batch_stride : (long long)D * OH * OW;
+  MFN_REQUIRE(obs >= (long long)D * OH * OW, MFN_ERR_INVALID_ARG, "mfn_correlation_forward: out_batch_stride too small");
+  MFN_REQUIRE((long long)N * C * H * W < (1LL << 40) && (long long)C * H * W < (1LL << 31), MFN_ERR_ALIGNMENT,
+              "mfn_correlation_forward: extents overflow kernel indexing");
+  cudaStream_t st = as_stream(stream);
+  const bool ref_regime = kernel_size == 1 && stride1 == 1 && stride2 == 1 && is_multiply &&
+                          pad_size == max_displacement && (max_displacement == 4 || max_displacement == 2);
+  if (algo == MFN_CORR_AUTO) algo = ref_regime ? (C >= 16 ? MFN_CORR_MMA_BF16X3 : MFN_CORR_SIMT) : MFN_CORR_GENERIC;
+  switch (algo) {
+    case MFN_CORR_GENERIC:
+      return launch_generic(data1, data2, out, N, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+                            is_multiply ? 1 : 0, D, OH, OW, obs, leaky_slope, st);
+    case MFN_CORR_SIMT:
+      MFN_REQUIRE(ref_regime, MFN_ERR_UNSUPPORTED,
+                  "mfn_correlation_forward: SIMT kernel needs kernel_size=1, strides=1, multiply, pad==md in {2,4}");
+      return max_displacement == 4 ? launch_simt<4>(data1, data2, out, N, C, H, W, obs, leaky_slope, st)
+                                   : launch_simt<2>(data1, data2, out, N, C, H, W, obs, leaky_slope, st);
+    case MFN_CORR_MMA_BF16X3:
+      MFN_REQUIRE(ref_regime, MFN_ERR_UNSUPPORTED,
+                  "mfn_correlation_forward: MMA kernel needs kernel_size=1, strides=1, multiply, pad==md in {2,4}");
+      return max_displacement == 4 ? launch_mma<4>(data1, data2, out, N, C, H, W, obs, leaky_slope, st)
+                                   : launch_mma<2>(data1, data2, out, N, C, H, W, obs, leaky_slope, st);
+    default:
+      return fail(MFN_ERR_INVALID_ARG, "mfn_correlation_forward: unknown algo %d", algo);
+  }
+}

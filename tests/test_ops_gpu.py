@@ -1,0 +1,304 @@
+"""GPU parity tests: every C-ABI entry point (through maskflownet_b200.ops) against the CPU oracle on identical seeded
+inputs.  Tolerances: exact-fp32 kernels 2e-5 (summation-order noise), the bf16x3 tensor-core correlation 1e-4 (the
+bound BASELINE.json's north_star states for fp32 parity)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref, torch_ref
+
+pytestmark = pytest.mark.gpu
+
+from maskflownet_b200 import ops, _lib  # noqa: E402
+
+DEV = "cuda"
+
+
+def feat(rng, shape):
+    """post-activation feature statistics: LeakyReLU_0.1(N(0,1))  """
+    a = rng.standard_normal(shape).astype(np.float32)
+    return np.where(a > 0, a, 0.1 * a).astype(np.float32)
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+CORR_SHAPES = [
+    (1, 196, 6, 8),      # BASELINE config[0]: level 6 of a 384x512 pair
+    (2, 32, 24, 40),     # vector path, two x-tiles, partial tiles in y
+    (1, 64, 13, 20),     # C=64 (two channel chunks), ragged rows
+    (2, 16, 9, 15),      # W % 4 != 0 -> scalar producer path (cfg5 level 6 is 9x15)
+    (1, 35, 7, 16),      # C not a multiple of 16/32
+    (1, 96, 28, 64),     # level 4 of cfg2
+    (3, 8, 5, 3),        # tiny, narrower than the halo
+]
+
+
+@pytest.mark.parametrize("shape", CORR_SHAPES)
+@pytest.mark.parametrize("md", [4, 2])
+@pytest.mark.parametrize("algo,tol", [(ops.CORR_GENERIC, 2e-5), (ops.CORR_SIMT, 2e-5), (ops.CORR_MMA_BF16X3, 1e-4)])
+def test_correlation_parity(shape, md, algo, tol):
+    rng = np.random.default_rng(hash((shape, md)) % (2 ** 31))
+    f1, f2 = feat(rng, shape), feat(rng, shape)
+    ref = cref.correlation_forward(f1, f2, pad_size=md, max_displacement=md, threads=8)
+    got = ops.correlation(cu(f1), cu(f2), pad_size=md, max_displacement=md, algo=algo).cpu().numpy()
+    assert got.shape == ref.shape
+    err = np.abs(got - ref).max()
+    assert err <= tol, (err, _lib.last_kernel())
+
+
+@pytest.mark.parametrize("algo", [ops.CORR_GENERIC, ops.CORR_SIMT, ops.CORR_MMA_BF16X3])
+def test_correlation_fused_leaky_and_concat_slot(algo):
+    rng = np.random.default_rng(5)
+    f1, f2 = feat(rng, (2, 32, 12, 32)), feat(rng, (2, 32, 12, 32))
+    ref = cref.correlation_forward(f1, f2)
+    ref = np.where(ref > 0, ref, 0.1 * ref)
+    buf = torch.full((2, 81 + 7, 12, 32), -7.0, device=DEV)
+    ops.correlation(cu(f1), cu(f2), leaky_slope=0.1, algo=algo, out=buf[:, :81])
+    got = buf.cpu().numpy()
+    assert np.abs(got[:, :81] - ref).max() <= 1e-4
+    assert (got[:, 81:] == -7.0).all()  # the rest of the concat buffer is untouched
+
+
+@pytest.mark.parametrize("k,md,s1,s2,pad,mul", [(1, 3, 1, 1, 3, 1), (3, 4, 2, 2, 5, 1), (1, 3, 1, 1, 3, 0),
+                                               (3, 2, 1, 1, 3, 0), (1, 4, 2, 1, 4, 1), (1, 4, 1, 2, 4, 1),
+                                               (1, 2, 1, 1, 4, 1)])
+def test_correlation_generic_parameters(k, md, s1, s2, pad, mul):
+    rng = np.random.default_rng(11)
+    f1, f2 = feat(rng, (2, 5, 9, 11)), feat(rng, (2, 5, 9, 11))
+    ref = cref.correlation_forward(f1, f2, pad, k, md, s1, s2, mul)
+    got = ops.correlation(cu(f1), cu(f2), pad, k, md, s1, s2, mul).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-5
+
+
+def test_correlation_known_answers():
+    # ones -> indicator of in-range displacement; shifted copy -> channel q0 equals mean_c f^2
+    one = torch.ones(1, 32, 10, 16, device=DEV)
+    out = ops.correlation(one, one).cpu().numpy()
+    for q in range(81):
+        dy, dx = q // 9 - 4, q % 9 - 4
+        exp = np.zeros((10, 16), np.float32)
+        exp[max(0, -dy):10 - max(0, dy), max(0, -dx):16 - max(0, dx)] = 1
+        assert np.abs(out[0, q] - exp).max() <= 1e-5
+    rng = np.random.default_rng(2)
+    f = feat(rng, (1, 32, 12, 16))
+    sh = np.zeros_like(f)
+    sh[:, :, 2:, :-3] = f[:, :, :-2, 3:]  # f2[y,x] = f1[y-2, x+3]  => best match at (dy,dx) = (2,-3)
+    out = ops.correlation(cu(f), cu(sh)).cpu().numpy()
+    q0 = (2 + 4) * 9 + (-3 + 4)
+    exp = (f ** 2).mean(1)[0]
+    assert np.abs(out[0, q0, :-2, 3:] - exp[:-2, 3:]).max() <= 1e-4
+    # md=2 volume is the central 5x5 block of the md=4 volume
+    a4 = ops.correlation(cu(f), cu(sh), algo=ops.CORR_SIMT).cpu().numpy().reshape(1, 9, 9, 12, 16)
+    a2 = ops.correlation(cu(f), cu(sh), pad_size=2, max_displacement=2, algo=ops.CORR_SIMT).cpu().numpy()
+    assert np.abs(a4[:, 2:7, 2:7].reshape(1, 25, 12, 16) - a2).max() <= 1e-6
+
+
+def test_correlation_full_size_properties():
+    """BASELINE config[1] level-2 size (8,32,112,256): all three kernels agree, plus linearity in data2."""
+    g = torch.Generator(device=DEV).manual_seed(0)
+    f1 = torch.nn.functional.leaky_relu(torch.randn(8, 32, 112, 256, device=DEV, generator=g), 0.1)
+    f2 = torch.nn.functional.leaky_relu(torch.randn(8, 32, 112, 256, device=DEV, generator=g), 0.1)
+    a = ops.correlation(f1, f2, algo=ops.CORR_SIMT)
+    b = ops.correlation(f1, f2, algo=ops.CORR_MMA_BF16X3)
+    c = ops.correlation(f1, f2, algo=ops.CORR_GENERIC)
+    assert (a - c).abs().max().item() <= 2e-5
+    assert (a - b).abs().max().item() <= 1e-4
+    lin = ops.correlation(f1, 2.0 * f2, algo=ops.CORR_MMA_BF16X3)
+    assert (lin - 2.0 * b).abs().max().item() <= 2e-4
+    # oracle on one sample of the batch
+    ref = cref.correlation_forward(f1[3:4].cpu().numpy(), f2[3:4].cpu().numpy(), threads=8)
+    assert np.abs(b[3:4].cpu().numpy() - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 12, 20), (1, 16, 9, 15)])
+@pytest.mark.parametrize("md", [4, 2])
+@pytest.mark.parametrize("slope", [1.0, 0.1])
+def test_correlation_backward(shape, md, slope):
+    rng = np.random.default_rng(7)
+    f1, f2 = feat(rng, shape), feat(rng, shape)
+    G = 2 * md + 1
+    go = rng.standard_normal((shape[0], G * G, shape[2], shape[3])).astype(np.float32)
+    t1, t2 = cu(f1).requires_grad_(), cu(f2).requires_grad_()
+    out = ops.correlation(t1, t2, pad_size=md, max_displacement=md, leaky_slope=slope, algo=ops.CORR_SIMT)
+    out.backward(cu(go))
+    fwd = cref.correlation_forward(f1, f2, pad_size=md, max_displacement=md)
+    go_eff = go * np.where(fwd > 0, 1.0, slope).astype(np.float32)
+    r1, r2 = cref.correlation_backward(go_eff, f1, f2, md)
+    assert np.abs(t1.grad.cpu().numpy() - r1).max() <= 5e-5
+    assert np.abs(t2.grad.cpu().numpy() - r2).max() <= 5e-5
+
+
+# ------------------------------------------------------------------------------------------------------------
+# deformable convolution / fused warp
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,C,F,H,W", [(2, 6, 5, 12, 14), (1, 32, 32, 10, 16), (1, 20, 70, 7, 9), (1, 196, 196, 6, 8)])
+@pytest.mark.parametrize("border", [0, 1])
+@pytest.mark.parametrize("bias", [True, False])
+def test_deformable_conv_forward(N, C, F, H, W, border, bias):
+    rng = np.random.default_rng(3)
+    x = feat(rng, (N, C, H, W))
+    w = (rng.standard_normal((F, C, 3, 3)) * np.sqrt(2.0 / (9 * C))).astype(np.float32)
+    b = rng.standard_normal(F).astype(np.float32) if bias else None
+    off = (rng.standard_normal((N, 18, H, W)) * 2.5).astype(np.float32)  # many taps leave the image
+    ref = cref.deformable_conv_forward(x, off, w, b, border_mode=border, threads=8)
+    got = ops.deformable_convolution(cu(x), cu(off), cu(w), cu(b) if bias else None, no_bias=not bias,
+                                     border_mode=border).cpu().numpy()
+    assert np.abs(got - ref).max() <= 3e-5
+
+
+def _level_inputs(rng, N, C, F, H, W, up=2):
+    x = feat(rng, (N, C, H, W))
+    w = (rng.standard_normal((F, C, 3, 3)) * np.sqrt(2.0 / (9 * C))).astype(np.float32)
+    b = (rng.standard_normal(F) * 0.1).astype(np.float32)
+    flow = (rng.standard_normal((N, 2, H // up, W // up)) * 0.4).astype(np.float32)  # x20/stride -> a few px
+    mask = (rng.standard_normal((N, 1, H // up, W // up)) + 0.5).astype(np.float32)
+    trade = (rng.standard_normal((N, F, H, W)) * 0.3).astype(np.float32)
+    return x, w, b, flow, mask, trade
+
+
+@pytest.mark.parametrize("N,C,F,H,W", [(2, 32, 32, 12, 16), (1, 64, 64, 8, 12), (1, 96, 96, 6, 8)])
+@pytest.mark.parametrize("border", [0, 1])
+def test_warp_mask_forward(N, C, F, H, W, border):
+    rng = np.random.default_rng(4)
+    x, w, b, flow, mask, trade = _level_inputs(rng, N, C, F, H, W)
+    t = torch.from_numpy
+    ref, rflow, rmask = torch_ref.warp_mask(t(x), t(flow), t(mask), t(w), t(b), t(trade), 20.0, 4, 2, border)
+    out, fup, mup = ops.warp_mask(cu(x), cu(flow), cu(mask), cu(w), cu(b), cu(trade), 20.0, 4.0, 2, 0.1, border)
+    assert np.abs(fup.cpu().numpy() - rflow.numpy()).max() <= 1e-6
+    assert np.abs(mup.cpu().numpy() - rmask.numpy()).max() <= 1e-6
+    assert np.abs(out.cpu().numpy() - ref.numpy()).max() <= 5e-5
+    # cross-check the oracle's two implementations on the same case (C forward with explicit 18-ch offsets)
+    offs = np.repeat((rflow.numpy() * 20.0 / 4)[:, None], 9, 1).reshape(N, 18, H, W)
+    conv = cref.deformable_conv_forward(x, offs, w, b, border_mode=border)
+    sig = 1 / (1 + np.exp(-rmask.numpy()))
+    pre = conv * sig + trade
+    assert np.abs(np.where(pre > 0, pre, 0.1 * pre) - ref.numpy()).max() <= 5e-5
+
+
+def test_warp_mask_cascade_variant():
+    """cascade: no mask, no trade-off, level 6 has no upsampling (network/MaskFlownet.py:463-466)"""
+    rng = np.random.default_rng(6)
+    x, w, b, flow, _, _ = _level_inputs(rng, 2, 24, 24, 7, 16, up=1)
+    t = torch.from_numpy
+    ref, _, _ = torch_ref.warp_mask(t(x), t(flow), None, t(w), t(b), None, 20.0, 64, 1, 0)
+    out, fup, mup = ops.warp_mask(cu(x), cu(flow), None, cu(w), cu(b), None, 20.0, 64.0, 1, 0.1, 0)
+    assert mup is None
+    assert np.abs(out.cpu().numpy() - ref.numpy()).max() <= 5e-5
+    assert np.abs(fup.cpu().numpy() - flow).max() == 0
+
+
+@pytest.mark.parametrize("border", [0, 1])
+def test_deformable_conv_backward(border):
+    rng = np.random.default_rng(8)
+    N, C, F, H, W = 2, 10, 7, 9, 11
+    x = feat(rng, (N, C, H, W))
+    w = (rng.standard_normal((F, C, 3, 3)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(F).astype(np.float32)
+    off = (rng.standard_normal((N, 18, H, W)) * 1.5).astype(np.float32)
+    go = rng.standard_normal((N, F, H, W)).astype(np.float32)
+    rt = [torch.from_numpy(a).clone().requires_grad_() for a in (x, off, w, b)]
+    torch_ref.deformable_conv(*rt, border).backward(torch.from_numpy(go))
+    gt = [cu(a).requires_grad_() for a in (x, off, w, b)]
+    ops.deformable_convolution(gt[0], gt[1], gt[2], gt[3], border_mode=border).backward(cu(go))
+    for name, r, g in zip("x offset weight bias".split(), rt, gt):
+        err = (g.grad.cpu() - r.grad).abs().max().item()
+        scale = max(1.0, r.grad.abs().max().item())
+        assert err <= 2e-4 * scale, (name, err, scale)
+
+
+@pytest.mark.parametrize("border", [0, 1])
+@pytest.mark.parametrize("with_mask", [True, False])
+def test_warp_mask_backward(border, with_mask):
+    rng = np.random.default_rng(9)
+    N, C, F, H, W = 2, 12, 12, 8, 12
+    x, w, b, flow, mask, trade = _level_inputs(rng, N, C, F, H, W)
+    go = rng.standard_normal((N, F, H, W)).astype(np.float32)
+    gflow = rng.standard_normal((N, 2, H, W)).astype(np.float32)  # the decoder also consumes the up-sampled flow
+    names = ["x", "flow", "mask", "w", "b", "trade"] if with_mask else ["x", "flow", "w", "b"]
+    arrs = [x, flow, mask, w, b, trade] if with_mask else [x, flow, w, b]
+    rt = [torch.from_numpy(a).clone().requires_grad_() for a in arrs]
+    gt = [cu(a).requires_grad_() for a in arrs]
+    if with_mask:
+        ro, rf, _ = torch_ref.warp_mask(rt[0], rt[1], rt[2], rt[3], rt[4], rt[5], 20.0, 8, 2, border)
+        go_, gf, _ = ops.warp_mask(gt[0], gt[1], gt[2], gt[3], gt[4], gt[5], 20.0, 8.0, 2, 0.1, border)
+    else:
+        ro, rf, _ = torch_ref.warp_mask(rt[0], rt[1], None, rt[2], rt[3], None, 20.0, 8, 2, border)
+        go_, gf, _ = ops.warp_mask(gt[0], gt[1], None, gt[2], gt[3], None, 20.0, 8.0, 2, 0.1, border)
+    ((ro * torch.from_numpy(go)).sum() + (rf * torch.from_numpy(gflow)).sum()).backward()
+    ((go_ * cu(go)).sum() + (gf * cu(gflow)).sum()).backward()
+    for name, r, g in zip(names, rt, gt):
+        err = (g.grad.cpu() - r.grad).abs().max().item()
+        scale = max(1.0, r.grad.abs().max().item())
+        assert err <= 2e-4 * scale, (name, err, scale)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Upsample / image warp
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("factor", [2, 4])
+def test_upsample_forward_backward(factor):
+    rng = np.random.default_rng(10)
+    u = rng.standard_normal((2, 3, 5, 7)).astype(np.float32)
+    ref = cref.upsample(u, factor)
+    t = cu(u).requires_grad_()
+    got = ops.upsample(t, factor)
+    assert np.abs(got.detach().cpu().numpy() - ref).max() <= 1e-6
+    go = rng.standard_normal(ref.shape).astype(np.float32)
+    got.backward(cu(go))
+    r = torch.from_numpy(u).clone().requires_grad_()
+    torch_ref.upsample(r, factor).backward(torch.from_numpy(go))
+    assert (t.grad.cpu() - r.grad).abs().max().item() <= 1e-5
+
+
+def test_grid_generator_and_sampler():
+    rng = np.random.default_rng(12)
+    img = rng.standard_normal((2, 3, 10, 12)).astype(np.float32)
+    fl = (rng.standard_normal((2, 2, 10, 12)) * 3).astype(np.float32)
+    grid_ref = cref.grid_generator_warp(fl)
+    grid = ops.grid_generator_warp(cu(fl))
+    assert np.abs(grid.cpu().numpy() - grid_ref).max() <= 1e-6
+    out = ops.bilinear_sampler(cu(img), grid).cpu().numpy()
+    assert np.abs(out - cref.bilinear_sampler(img, grid_ref)).max() <= 2e-5
+    rec = ops.reconstruction2d(cu(img), cu(fl)).cpu().numpy()
+    assert np.abs(rec - cref.reconstruction2d(img, fl)).max() <= 2e-5
+
+
+def test_image_warp_concat():
+    rng = np.random.default_rng(13)
+    N, H, W = 2, 16, 24
+    im1 = rng.random((N, 3, H, W)).astype(np.float32)
+    im2 = rng.random((N, 3, H, W)).astype(np.float32)
+    fq = (rng.standard_normal((N, 2, H // 4, W // 4)) * 0.2).astype(np.float32)
+    mq = rng.standard_normal((N, 1, H // 4, W // 4)).astype(np.float32)
+    ref = torch_ref.image_warp_concat(torch.from_numpy(im2), torch.from_numpy(fq), torch.from_numpy(mq), 20.0).numpy()
+    c30, c40 = ops.image_warp_concat(cu(im1), cu(im2), cu(fq), cu(mq), 20.0)
+    assert np.abs(c40.cpu().numpy() - ref).max() <= 3e-5
+    c30 = c30.cpu().numpy()
+    assert (c30[:, :3] == im1).all() and (c30[:, 3] == 0).all()
+
+
+def test_errors_are_loud():
+    from maskflownet_b200 import MaskflowError
+    a = torch.zeros(1, 4, 4, 4, device=DEV)
+    with pytest.raises(MaskflowError):
+        ops.correlation(a, torch.zeros(1, 4, 4, 5, device=DEV))
+    with pytest.raises(MaskflowError):
+        ops.correlation(a, a, kernel_size=2)
+    with pytest.raises(MaskflowError):
+        ops.correlation(a, a, algo=ops.CORR_MMA_BF16X3, stride1=2)
+    with pytest.raises(MaskflowError):
+        ops.correlation(a.cpu(), a.cpu())
+    with pytest.raises(MaskflowError):
+        ops.deformable_convolution(a, torch.zeros(1, 18, 4, 4, device=DEV), torch.zeros(4, 4, 3, 3, device=DEV),
+                                   kernel=(5, 5))
+
+
+def test_native_launch_counter_moves():
+    a = torch.ones(1, 16, 8, 8, device=DEV)
+    n0 = _lib.launch_count()
+    ops.correlation(a, a)
+    assert _lib.launch_count() == n0 + 1
+    assert "corr_mma_kernel" in _lib.last_kernel()
