@@ -1,0 +1,255 @@
+"""Host-side mirror of the reference's model graphs, calling the fused B200 operators.
+
+`MaskFlownetS` computes what `MaskFlownet_S.hybrid_forward` computes (network/MaskFlownet.py:197-315) and
+`MaskFlownet` what the cascade computes (:443-545), but is organised around the hot path instead of transcribing the
+unrolled reference code: one loop over pyramid levels in which
+
+    Upsample(2) flow/mask + offset build + DeformableConvolution + sigmoid-mask multiply + trade-off + LeakyReLU
+        (MaskFlownet.py:228-233)                                   -> one launch of ops.warp_mask      (K3)
+    Correlation + LeakyReLU (:234-235), written straight into its slot of the decoder's concat buffer (:236)
+                                                                    -> one launch of ops.correlation    (K1)
+    Upsample(4) + GridGenerator + BilinearSampler + sigmoid-0.5 + concat (:308-313)
+                                                                    -> one launch of ops.image_warp_concat (K5)
+
+The dense 3x3 convolutions (about 98 % of the FLOPs) are outside the hot-path scope and stay on
+cuDNN through torch.nn.functional.  Sub-module names equal the reference's gluon prefixes (conv1a ... deform5, conv5f,
+dc_conv7 ...) so that shipped .params checkpoints map by name (maskflownet_b200.params).
+
+All flows are (y, x)-ordered and in units of pixels/scale, as in the reference (pipeline.py:105, MaskFlownet.py:69).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as tF
+
+from . import ops
+
+PYRAMID_CH = {1: 16, 2: 32, 3: 64, 4: 96, 5: 128, 6: 196}   # network/MaskFlownet.py:79-96
+DECODER_CH = (128, 128, 96, 64, 32)                           # convL_0 .. convL_4 (:102-130)
+STRIDES = {6: 64, 5: 32, 4: 16, 3: 8, 2: 4}                   # self.strides (:71)
+SLOPE = 0.1
+
+
+def _conv(cin, cout, k=3, s=1, p=1, d=1):
+    return nn.Conv2d(cin, cout, k, s, p, d)
+
+
+def msra_prelu_init_(module: nn.Module, slope: float = SLOPE, seed: Optional[int] = None) -> None:
+    """MSRAPrelu(factor_type='avg', slope) for weights, zeros for biases -- the reference's initialiser
+    (network/pipeline.py:26)."""
+    gen = torch.Generator().manual_seed(seed) if seed is not None else None
+    for name, p in module.named_parameters():
+        if p.dim() < 2:
+            with torch.no_grad():
+                p.zero_()
+            continue
+        hw = 1
+        for d in p.shape[2:]:
+            hw *= d
+        fan_in, fan_out = p.shape[1] * hw, p.shape[0] * hw
+        std = math.sqrt(2.0 / ((1 + slope ** 2) * (fan_in + fan_out) / 2.0))
+        with torch.no_grad():
+            p.copy_((torch.randn(p.shape, generator=gen) * std).to(p.device))
+
+
+class DeformParams(nn.Module):
+    """Weights of one layer.DeformableConv2D block (network/layer.py:32-110): weight (F, C, 3, 3) and bias (F)."""
+
+    def __init__(self, channels: int, use_bias: bool = True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(channels, channels, 3, 3))
+        self.bias = nn.Parameter(torch.zeros(channels)) if use_bias else None
+
+
+class _FlowNetBase(nn.Module):
+    def _pyramid(self, x, names):
+        feats = []
+        for lvl in range(1, 7):
+            for sfx in names:
+                x = tF.leaky_relu(getattr(self, f"conv{lvl}{sfx}")(x), SLOPE)
+            feats.append(x)
+        return feats  # [c?1 .. c?6]
+
+    def _dense(self, lvl, x):
+        for i in range(5):
+            x = torch.cat([tF.leaky_relu(getattr(self, f"conv{lvl}_{i}")(x), SLOPE), x], dim=1)
+        return x
+
+    def _context(self, x):
+        for i in range(1, 7):
+            x = tF.leaky_relu(getattr(self, f"dc_conv{i}")(x), SLOPE)
+        return self.dc_conv7(x)
+
+    def _make_decoder(self, in_ch: Dict[int, int], with_mask: bool, upfeat_ch):
+        for lvl in (6, 5, 4, 3, 2):
+            c = in_ch[lvl]
+            for i, oc in enumerate(DECODER_CH):
+                setattr(self, f"conv{lvl}_{i}", _conv(c, oc))
+                c += oc
+            setattr(self, f"pred_flow{lvl}", _conv(c, 2))
+            if with_mask and lvl > 2:
+                setattr(self, f"pred_mask{lvl}", _conv(c, 1))
+            if lvl > 2:
+                setattr(self, f"upfeat{lvl - 1}", nn.ConvTranspose2d(c, upfeat_ch[5 - lvl + 0] if False else upfeat_ch[6 - lvl - 1 + 0], 4, 2, 1))
+        c2 = in_ch[2] + sum(DECODER_CH)
+        dil = (1, 2, 4, 8, 16, 1)
+        chs = (128, 128, 128, 96, 64, 32)
+        c = c2
+        for i in range(6):
+            setattr(self, f"dc_conv{i + 1}", _conv(c, chs[i], 3, 1, dil[i], dil[i]))
+            c = chs[i]
+        self.dc_conv7 = _conv(c, 2)
+
+
+class MaskFlownetS(_FlowNetBase):
+    """MaskFlownet-S (reference class MaskFlownet_S, network/MaskFlownet.py:66-315)."""
+
+    def __init__(self, flow_multiplier: float = 1.0, deform_bias: bool = True, upfeat_ch=(16, 16, 16, 16),
+                 border_mode: int = ops.BORDER_MXNET15):
+        super().__init__()
+        self.scale = 20.0 * flow_multiplier
+        self.md = 4
+        self.border_mode = border_mode
+        self.upfeat_ch = tuple(upfeat_ch)
+        cin = 3
+        for lvl in range(1, 7):
+            co = PYRAMID_CH[lvl]
+            setattr(self, f"conv{lvl}a", _conv(cin, co, 3, 2))
+            setattr(self, f"conv{lvl}b", _conv(co, co))
+            setattr(self, f"conv{lvl}c", _conv(co, co))
+            cin = co
+        D = (2 * self.md + 1) ** 2
+        in_ch = {6: D}
+        for i, lvl in enumerate((5, 4, 3, 2)):
+            in_ch[lvl] = D + PYRAMID_CH[lvl] + self.upfeat_ch[i] + 2
+        self._make_decoder(in_ch, with_mask=True, upfeat_ch=self.upfeat_ch)
+        for i, lvl in enumerate((5, 4, 3, 2)):
+            setattr(self, f"deform{lvl}", DeformParams(PYRAMID_CH[lvl], deform_bias))
+            setattr(self, f"conv{lvl}f", _conv(self.upfeat_ch[i], PYRAMID_CH[lvl]))
+        msra_prelu_init_(self)
+
+    # one correlation + its consumers' concat buffer: [corr | extras...]
+    def _corr_block(self, f1, f2, extras: List[torch.Tensor]):
+        N, _, H, W = f1.shape
+        D = (2 * self.md + 1) ** 2
+        if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
+            corr = ops.correlation(f1, f2, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE)
+            return torch.cat([corr] + extras, dim=1) if extras else corr
+        tot = D + sum(e.shape[1] for e in extras)
+        buf = torch.empty((N, tot, H, W), device=f1.device, dtype=torch.float32)
+        ops.correlation(f1, f2, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE, out=buf[:, :D])
+        c = D
+        for e in extras:
+            buf[:, c:c + e.shape[1]].copy_(e)
+            c += e.shape[1]
+        return buf
+
+    def forward(self, im1: torch.Tensor, im2: torch.Tensor, want_cascade_inputs: bool = False):
+        """Returns (predictions [flow6..flow2, each * scale], [sigmoid(mask2)], srcs or None) like the reference
+        (network/MaskFlownet.py:302-315).  srcs (needed only by the cascade) is built when want_cascade_inputs."""
+        c1 = self._pyramid(im1, "abc")
+        c2 = self._pyramid(im2, "abc")
+        x = self._dense(6, self._corr_block(c1[5], c2[5], []))
+        flow = self.pred_flow6(x)
+        mask = self.pred_mask6(x)
+        flows = [flow]
+        for lvl in (5, 4, 3, 2):
+            feat = tF.leaky_relu(getattr(self, f"upfeat{lvl}")(x), SLOPE)
+            dp = getattr(self, f"deform{lvl}")
+            trade = getattr(self, f"conv{lvl}f")(feat)
+            warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, mask, dp.weight, dp.bias, trade, self.scale,
+                                             float(STRIDES[lvl]), 2, SLOPE, self.border_mode)
+            x = self._dense(lvl, self._corr_block(c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up]))
+            flow = flow_up + getattr(self, f"pred_flow{lvl}")(x)
+            if lvl > 2:
+                mask = getattr(self, f"pred_mask{lvl}")(x)
+            else:
+                mask_up2 = _  # Upsample(2)(mask3): the level-2 occlusion mask (network/MaskFlownet.py:283)
+            flows.append(flow)
+        flows[-1] = flow = flow + self._context(x)
+        preds = [f * self.scale for f in flows]
+        occ = [torch.sigmoid(mask_up2)]
+        srcs = None
+        if want_cascade_inputs:
+            c30, c40 = ops.image_warp_concat(im1, im2, flow, mask_up2, self.scale)
+            # quirk kept from the reference: levels 2 and 3 of c2s carry IMAGE-1 features (MaskFlownet.py:306)
+            c2s = [c2[0], c1[1], c1[2], c2[3], c2[4], c2[5]]
+            srcs = (c1, c2s, flows, c30, c40)
+        return preds, occ, srcs
+
+
+class MaskFlownet(_FlowNetBase):
+    """Full cascade (reference class MaskFlownet, network/MaskFlownet.py:318-545): the S head plus a second, dual
+    pyramid on [im1; 0] and [warp(im2); mask] with md=2 correlations."""
+
+    def __init__(self, flow_multiplier: float = 1.0, deform_bias: bool = True, upfeat_ch=(16, 16, 16, 16),
+                 border_mode: int = ops.BORDER_MXNET15):
+        super().__init__()
+        self.scale = 20.0 * flow_multiplier
+        self.md = 2
+        self.border_mode = border_mode
+        self.MaskFlownet_S = MaskFlownetS(flow_multiplier, deform_bias, upfeat_ch, border_mode)
+        cin = 4
+        for lvl in range(1, 7):
+            co = PYRAMID_CH[lvl]
+            setattr(self, f"conv{lvl}x", _conv(cin, co, 3, 2))
+            setattr(self, f"conv{lvl}y", _conv(co, co))
+            setattr(self, f"conv{lvl}z", _conv(co, co))
+            cin = co
+        D = (2 * self.md + 1) ** 2
+        in_ch = {6: 2 * D + 2}
+        for i, lvl in enumerate((5, 4, 3, 2)):
+            in_ch[lvl] = PYRAMID_CH[lvl] + upfeat_ch[i] + 2 * D + 4
+        self._make_decoder(in_ch, with_mask=False, upfeat_ch=tuple(upfeat_ch))
+        for lvl in (6, 5, 4, 3, 2):
+            setattr(self, f"deform{lvl}", DeformParams(PYRAMID_CH[lvl], deform_bias))
+        msra_prelu_init_(self)
+
+    def _corr(self, a, b):
+        return ops.correlation(a, b, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE)
+
+    def forward(self, im1, im2):
+        _, _, srcs = self.MaskFlownet_S(im1, im2, want_cascade_inputs=True)
+        c1, c2, flows_s, c30, c40 = srcs
+        c3 = self._pyramid(c30, "xyz")
+        c4 = self._pyramid(c40, "xyz")
+        flow = flows_s[0]
+        dp = self.deform6
+        warp, _, _ = ops.warp_mask(c2[5], flow, None, dp.weight, dp.bias, None, self.scale, float(STRIDES[6]), 1,
+                                   SLOPE, self.border_mode)
+        x = self._dense(6, torch.cat([self._corr(c1[5], warp), self._corr(c3[5], c4[5]), flow], dim=1))
+        flow = flow + self.pred_flow6(x)
+        flows = [flow]
+        for i, lvl in enumerate((5, 4, 3, 2)):
+            feat = tF.leaky_relu(getattr(self, f"upfeat{lvl}")(x), SLOPE)
+            dp = getattr(self, f"deform{lvl}")
+            warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, None, dp.weight, dp.bias, None, self.scale,
+                                             float(STRIDES[lvl]), 2, SLOPE, self.border_mode)
+            x = self._dense(lvl, torch.cat([c1[lvl - 1], feat, self._corr(c1[lvl - 1], warp),
+                                            self._corr(c3[lvl - 1], c4[lvl - 1]), flow_up, flows_s[i + 1]], dim=1))
+            flow = flow_up + getattr(self, f"pred_flow{lvl}")(x)
+            flows.append(flow)
+        flows[-1] = flow = flow + self._context(x)
+        return [f * self.scale for f in flows], [flow[:, 0:1]], []
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the step either side of the network: what PipelineFlownet.do_batch does around it (network/pipeline.py:85-87,117-147)
+# ---------------------------------------------------------------------------------------------------------------
+def centralize(img1: torch.Tensor, img2: torch.Tensor):
+    """Subtract the per-sample RGB mean over both images (network/pipeline.py:85-87)."""
+    mean = torch.cat([img1, img2], dim=2).mean(dim=(2, 3), keepdim=True)
+    return img1 - mean, img2 - mean, mean
+
+
+@torch.no_grad()
+def predict_flow(net: nn.Module, img1_u8: torch.Tensor, img2_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 image pairs (N,3,H,W), H and W multiples of 64 -> full-resolution flow (N,2,H,W), (y,x)-ordered, in pixels:
+    /255, centralize, network, Upsample(4) of the finest prediction (network/pipeline.py:99,117-138)."""
+    a, b, _ = centralize(img1_u8.float() / 255.0, img2_u8.float() / 255.0)
+    preds = net(a, b)[0]
+    return ops.upsample(preds[-1], 4)
