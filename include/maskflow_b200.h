@@ -54,6 +54,9 @@ MFN_API const char* mfn_last_error(void);
 MFN_API const char* mfn_last_kernel(void);
 /* Number of kernel launches issued by this library since load (process-wide, monotonically increasing). */
 MFN_API unsigned long long mfn_launch_count(void);
+/* Process-wide tuning / test knobs.  Keys: "corr_grid_cap" (>0 caps the persistent grid of the tensor-core correlation
+ * kernels; tests use it to force long per-CTA tile runs), "corr_disable_ring" (1 = never pick the strip-marching kernel). */
+MFN_API int mfn_set_tuning(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------------
  * Correlation cost volume.

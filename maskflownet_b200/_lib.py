@@ -31,6 +31,7 @@ SIGNATURES = {
     "mfn_grid_generator_warp_forward": [_f, _f, _i, _i, _i, _f],
     "mfn_bilinear_sampler_forward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "mfn_image_warp_concat_forward": [_f] * 6 + [_i] * 4 + [_fl, _f],
+    "mfn_set_tuning": [ctypes.c_char_p, _i],
 }
 
 
@@ -84,3 +85,7 @@ def call(name: str, *args) -> None:
     if rc != 0:
         kind = "argument/support error" if rc < 0 else "CUDA error"
         raise MaskflowError(f"{name} failed ({kind} {rc}): {last_error()}")
+
+
+def set_tuning(key: str, value: int) -> None:
+    call("mfn_set_tuning", key.encode(), int(value))

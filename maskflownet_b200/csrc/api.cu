@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -22,6 +23,11 @@ int fail(int code, const char* fmt, ...) {
 
 void note_kernel(const char* name) { g_kernel = name; }
 
+Tuning& tuning() {
+  static Tuning t;
+  return t;
+}
+
 int check_launch(const char* kernel_name) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, "%s: launch failed: %s", kernel_name, cudaGetErrorString(e));
@@ -37,3 +43,11 @@ extern "C" int mfn_version(void) { return MFN_VERSION; }
 extern "C" const char* mfn_last_error(void) { return mfn::g_err; }
 extern "C" const char* mfn_last_kernel(void) { return mfn::g_kernel; }
 extern "C" unsigned long long mfn_launch_count(void) { return mfn::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int mfn_set_tuning(const char* key, int value) {
+  if (!key) return mfn::fail(MFN_ERR_INVALID_ARG, "mfn_set_tuning: null key");
+  if (!strcmp(key, "corr_grid_cap")) mfn::tuning().corr_grid_cap = value;
+  else if (!strcmp(key, "corr_disable_ring")) mfn::tuning().corr_disable_ring = value;
+  else return mfn::fail(MFN_ERR_INVALID_ARG, "mfn_set_tuning: unknown key '%s'", key);
+  return MFN_OK;
+}

@@ -12,6 +12,13 @@ int fail(int code, const char* fmt, ...);
 int check_launch(const char* kernel_name);  // cudaGetLastError -> return code, bumps launch counter
 void note_kernel(const char* name);
 
+// process-wide tuning / test knobs (mfn_set_tuning)
+struct Tuning {
+  int corr_grid_cap = 0;      // > 0: cap the persistent grid of the MMA correlation kernels (tests force long tile runs)
+  int corr_disable_ring = 0;  // 1: use the tile kernel even for C <= 32
+};
+Tuning& tuning();
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 #define MFN_REQUIRE(cond, code, ...)                   \

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1)
         const bool c_ok0 = ca < C, c_ok1 = ca + 1 < C;
         const float* pc = base + (size_t)ca * plane;
         constexpr int NOR = HR * OCT_PER_ROW;  // octet-rows in this stage
-        constexpr int U = 3;
+        constexpr int U = 7;  // 14 independent 16-byte loads per thread in flight
         for (int o0 = pw; o0 < NOR; o0 += NPROD * U) {
           float4 v0[U], v1[U];
           int pxr[U], rr[U];
@@ -426,6 +426,259 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1)
 }
 
 // =====================================================================================================
+// Tensor-core kernel, strip-marching variant for C <= 32 (one channel chunk): the dominant levels.
+//
+// A CTA owns a contiguous run of tiles in (n, x-strip, y) order and marches down each strip.  The split bf16 rows
+// of data2 live in a ring of R row slots, so a tile that continues a strip loads only its TH new rows (the 2*MD
+// halo rows above are still resident), all of them in one batch of independent 16-byte loads per producer thread
+// (enough bytes in flight to cover HBM latency).  Three tiles are in flight: consumers on tile s, producers up to
+// tile s+2.  Consumers prefetch the data1 fragments of the next tile into registers before starting the MMAs of the
+// current one, and run the displacement rows in two passes to keep the accumulator footprint at 40 registers.
+// =====================================================================================================
+namespace tcr {
+using namespace tc;
+constexpr int R = TH + 2 * 4 + 2 * TH;  // 26 row slots: 14 (tile s) + 6 (tile s+1) + 6 (tile s+2)
+constexpr int NSTAGE = 3;
+constexpr int ROW_BYTES = HWP * RS;       // one split row (hi or lo): 40 px * 80 B
+constexpr int LO_OFF = R * ROW_BYTES;
+constexpr int PASS = 5;                   // displacement rows per accumulator pass
+__host__ __device__ constexpr int ring_smem_bytes(int md) {
+  return 2 * R * ROW_BYTES + NCONS * (2 * md + 1) * STG_STRIDE * 4 + 64;
+}
+}  // namespace tcr
+
+template <int MD, bool VEC>
+__global__ void __launch_bounds__(tc::NTHREADS, 1)
+    corr_mma_ring_kernel(const float* __restrict__ d1, const float* __restrict__ d2, float* __restrict__ out,
+                         int N, int C, int H, int W, long long out_bs, float slope, int tilesX, int tilesY,
+                         int numTiles) {
+  using namespace tcr;
+  constexpr int G = 2 * MD + 1;
+  constexpr int HR = TH + 2 * MD;   // halo rows of one tile
+  constexpr int NEWR = TH;          // rows a continuing tile has to load
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;
+  float* stg_all = reinterpret_cast<float*>(smem_raw + 2 * R * ROW_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * R * ROW_BYTES + NCONS * G * STG_STRIDE * 4);
+  const uint32_t bar_full = smem_u32(bars);               // [NSTAGE]
+  const uint32_t bar_empty = smem_u32(bars + NSTAGE);     // [NSTAGE]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(bar_full + 8 * i, NPROD * 32);
+      mbar_init(bar_empty + 8 * i, NCONS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // balanced contiguous tile range of this CTA; linear order = ((n * tilesX + tx) * tilesY + ty)
+  const int t_begin = (int)(((long long)numTiles * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)numTiles * (blockIdx.x + 1)) / gridDim.x);
+  const int nStages = t_end - t_begin;
+  const size_t plane = (size_t)H * W;
+
+  if (warp >= NCONS) {
+    // ================================ PRODUCERS ================================
+    const int pw = warp - NCONS;
+    const int m = lane >> 4, j = lane & 15;
+    const int ca = 2 * j;
+    const bool c_ok0 = ca < C, c_ok1 = ca + 1 < C;
+    int wr = 0;  // next free ring slot
+    for (int s = 0; s < nStages; ++s) {
+      const int tile = t_begin + s;
+      const int ty = tile % tilesY, tx = (tile / tilesY) % tilesX, n = tile / (tilesY * tilesX);
+      const int x0 = tx * TW, y0 = ty * TH;
+      const bool fresh = (s == 0) || (ty == 0);
+      // ring slots are recycled from tile s-3; a fresh strip additionally needs s-1 and s-2 drained
+      if (s >= 3) mbar_wait(bar_empty + 8 * ((s - 3) % NSTAGE), ((s - 3) / NSTAGE) & 1);
+      if (fresh) {
+        if (s >= 2) mbar_wait(bar_empty + 8 * ((s - 2) % NSTAGE), ((s - 2) / NSTAGE) & 1);
+        if (s >= 1) mbar_wait(bar_empty + 8 * ((s - 1) % NSTAGE), ((s - 1) / NSTAGE) & 1);
+      }
+      const int first_slot = fresh ? wr : (wr + R - 2 * MD) % R;
+      const int rr0 = fresh ? 0 : 2 * MD;           // first halo row to load
+      const int nrows = fresh ? HR : NEWR;
+      wr = (wr + nrows) % R;
+      const float* pc = d2 + ((size_t)n * C + ca) * plane;
+      const int NOR = nrows * OCT_PER_ROW;
+      constexpr int U = (NEWR * OCT_PER_ROW + NPROD - 1) / NPROD;  // 9: a continuing tile is one batch
+      for (int o0 = pw; o0 < NOR; o0 += NPROD * U) {
+        float4 v0[U], v1[U];
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) {
+          const int o = o0 + uu * NPROD;
+          v0[uu] = make_float4(0.f, 0.f, 0.f, 0.f);
+          v1[uu] = v0[uu];
+          const int rr = rr0 + o / OCT_PER_ROW;
+          const int oct = o % OCT_PER_ROW;
+          const int pxr = 8 * oct + 4 * m - HX;
+          const int y = y0 - MD + rr;
+          const int x = x0 - 8 + 8 * oct + 4 * m;
+          if (o < NOR && pxr >= 0 && pxr < HWP && y >= 0 && y < H) {
+            const float* p = pc + (size_t)y * W + x;
+            if (VEC) {
+              if (x >= 0 && x < W) {
+                if (c_ok0) v0[uu] = __ldg(reinterpret_cast<const float4*>(p));
+                if (c_ok1) v1[uu] = __ldg(reinterpret_cast<const float4*>(p + plane));
+              }
+            } else {
+              float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (x + e >= 0 && x + e < W) {
+                  if (c_ok0) t0[e] = __ldg(p + e);
+                  if (c_ok1) t1[e] = __ldg(p + plane + e);
+                }
+              v0[uu] = make_float4(t0[0], t0[1], t0[2], t0[3]);
+              v1[uu] = make_float4(t1[0], t1[1], t1[2], t1[3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) {
+          const int o = o0 + uu * NPROD;
+          const int rr = rr0 + o / OCT_PER_ROW;
+          const int oct = o % OCT_PER_ROW;
+          const int pxr = 8 * oct + 4 * m - HX;
+          if (o < NOR && pxr >= 0 && pxr < HWP) {
+            const int slot = (first_slot + rr) % R;
+            unsigned char* dst = ring + (size_t)slot * ROW_BYTES + pxr * RS + 4 * j;
+            const float a[4] = {v0[uu].x, v0[uu].y, v0[uu].z, v0[uu].w};
+            const float c[4] = {v1[uu].x, v1[uu].y, v1[uu].z, v1[uu].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint32_t hi, lo;
+              split_pair(a[e], c[e], hi, lo);
+              *reinterpret_cast<uint32_t*>(dst + e * RS) = hi;
+              *reinterpret_cast<uint32_t*>(dst + e * RS + LO_OFF) = lo;
+            }
+          }
+        }
+      }
+      mbar_arrive(bar_full + 8 * (s % NSTAGE));
+    }
+  } else {
+    // ================================ CONSUMERS ================================
+    const int r = warp >> 1;
+    const int xs = (warp & 1) * 16;
+    const int g = lane >> 2, j = lane & 3;
+    float* stg = stg_all + warp * (G * STG_STRIDE);
+    const float invC = 1.f / (float)C;
+    const int l8 = lane & 7, mi = lane >> 3;
+    const uint32_t off12 = (uint32_t)((xs + 8 * (mi & 1) + l8) * RS + 16 * (mi >> 1));
+    const uint32_t off3 = (uint32_t)((xs + 16 + l8) * RS + 16 * (mi & 1) + (mi >> 1) * LO_OFF);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const bool two_k = C > 16;
+
+    // raw data1 values of the NEXT tile (prefetched): [k-step][tile][e0,e1,e8,e9]
+    float raw[2][2][4];
+    auto load_raw = [&](int tile) {
+      const int ty = tile % tilesY, tx = (tile / tilesY) % tilesX, n = tile / (tilesY * tilesX);
+      const int y = ty * TH + r;
+      const float* f1n = d1 + (size_t)n * C * plane;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int x = tx * TW + xs + 8 * t + g;
+          const int c = 16 * kk + 2 * j;
+          const bool ok = (y < H) && (x < W);
+          const float* p = f1n + (size_t)c * plane + (size_t)y * W + x;
+          raw[kk][t][0] = (ok && c < C) ? __ldg(p) : 0.f;
+          raw[kk][t][1] = (ok && c + 1 < C) ? __ldg(p + plane) : 0.f;
+          raw[kk][t][2] = (ok && c + 8 < C) ? __ldg(p + 8 * plane) : 0.f;
+          raw[kk][t][3] = (ok && c + 9 < C) ? __ldg(p + 9 * plane) : 0.f;
+        }
+    };
+    if (nStages > 0) load_raw(t_begin);
+
+    int wr = 0;
+    for (int s = 0; s < nStages; ++s) {
+      const int tile = t_begin + s;
+      const int ty = tile % tilesY, tx = (tile / tilesY) % tilesX, n = tile / (tilesY * tilesX);
+      const int x0 = tx * TW, y0 = ty * TH;
+      const int y = y0 + r;
+      const bool fresh = (s == 0) || (ty == 0);
+      const int first_slot = fresh ? wr : (wr + R - 2 * MD) % R;
+      wr = (wr + (fresh ? HR : NEWR)) % R;
+
+      uint32_t bh[2][2][2], bl[2][2][2];
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          split_pair(raw[kk][t][0], raw[kk][t][1], bh[kk][t][0], bl[kk][t][0]);
+          split_pair(raw[kk][t][2], raw[kk][t][3], bh[kk][t][1], bl[kk][t][1]);
+        }
+      if (s + 1 < nStages) load_raw(tile + 1);  // in flight during this tile's MMAs
+
+      mbar_wait(bar_full + 8 * (s % NSTAGE), (s / NSTAGE) & 1);
+      float* obase = out + (size_t)n * out_bs + (size_t)y * W + (x0 + xs);
+      const int p = lane & 15, hsel = lane >> 4;
+      const int base_slot = first_slot + r;
+
+#pragma unroll
+      for (int d0 = 0; d0 < G; d0 += PASS) {
+        float acc[PASS][2][4];
+#pragma unroll
+        for (int d = 0; d < PASS; ++d)
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[d][t][i] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          if (kk == 1 && !two_k) break;
+#pragma unroll
+          for (int d = 0; d < PASS; ++d) {
+            if (d0 + d >= G) break;
+            int slot = base_slot + d0 + d;
+            if (slot >= R) slot -= R;
+            const uint32_t rowoff = ring_u32 + (uint32_t)(slot * ROW_BYTES + 32 * kk);
+            uint32_t h[4], l[4], x3[4];
+            ldsm_x4(rowoff + off12, h);
+            ldsm_x4(rowoff + off12 + LO_OFF, l);
+            ldsm_x4(rowoff + off3, x3);
+            mma_bf16(acc[d][0], h[0], h[1], h[2], h[3], bl[kk][0][0], bl[kk][0][1]);
+            mma_bf16(acc[d][0], l[0], l[1], l[2], l[3], bh[kk][0][0], bh[kk][0][1]);
+            mma_bf16(acc[d][0], h[0], h[1], h[2], h[3], bh[kk][0][0], bh[kk][0][1]);
+            mma_bf16(acc[d][1], h[1], x3[0], h[3], x3[1], bl[kk][1][0], bl[kk][1][1]);
+            mma_bf16(acc[d][1], l[1], x3[2], l[3], x3[3], bh[kk][1][0], bh[kk][1][1]);
+            mma_bf16(acc[d][1], h[1], x3[0], h[3], x3[1], bh[kk][1][0], bh[kk][1][1]);
+          }
+        }
+        if (d0 + PASS >= G) {  // last pass: every shared-memory read of this tile is done
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty + 8 * (s % NSTAGE));
+        }
+#pragma unroll
+        for (int d = 0; d < PASS; ++d) {
+          if (d0 + d >= G) break;
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = g + 8 * (i >> 1), col = 2 * j + (i & 1);
+              const int dxi = row - col - 4 + MD;
+              if (dxi >= 0 && dxi < G) stg[dxi * STG_STRIDE + 8 * t + col] = leaky(acc[d][t][i] * invC, slope);
+            }
+          __syncwarp();
+          if (y < H && x0 + xs + p < W) {
+#pragma unroll
+            for (int dxi = hsel; dxi < G; dxi += 2)
+              obase[(size_t)((d0 + d) * G + dxi) * plane + p] = stg[dxi * STG_STRIDE + p];
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+}
+
+// =====================================================================================================
 // Host dispatch
 // =====================================================================================================
 static int launch_generic(const float* d1, const float* d2, float* out, int N, int C, int H, int W, int pad,
@@ -470,17 +723,42 @@ static int launch_mma_impl(const float* d1, const float* d2, float* out, int N, 
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_mma_kernel): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  const int cap = tuning().corr_grid_cap > 0 ? tuning().corr_grid_cap : kNumSMs;
+  const int grid = (int)(tiles < cap ? tiles : cap);
   corr_mma_kernel<MD, VEC><<<grid, NTHREADS, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope, tilesX, tilesY,
                                                          (int)tiles);
   return check_launch(MD == 4 ? (VEC ? "corr_mma_kernel<4,vec>" : "corr_mma_kernel<4,scalar>")
                               : (VEC ? "corr_mma_kernel<2,vec>" : "corr_mma_kernel<2,scalar>"));
 }
 
+template <int MD, bool VEC>
+static int launch_mma_ring_impl(const float* d1, const float* d2, float* out, int N, int C, int H, int W,
+                                long long obs, float slope, cudaStream_t st) {
+  using namespace tcr;
+  const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
+  const long long tiles = (long long)N * tilesX * tilesY;
+  const int smem = ring_smem_bytes(MD);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(corr_mma_ring_kernel<MD, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_mma_ring_kernel): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int cap = tuning().corr_grid_cap > 0 ? tuning().corr_grid_cap : kNumSMs;
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  corr_mma_ring_kernel<MD, VEC><<<grid, NTHREADS, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope, tilesX, tilesY,
+                                                              (int)tiles);
+  return check_launch(MD == 4 ? (VEC ? "corr_mma_ring_kernel<4,vec>" : "corr_mma_ring_kernel<4,scalar>")
+                              : (VEC ? "corr_mma_ring_kernel<2,vec>" : "corr_mma_ring_kernel<2,scalar>"));
+}
+
 template <int MD>
 static int launch_mma(const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,
                       float slope, cudaStream_t st) {
   const bool vec = (W % 4 == 0) && aligned(d2, 16);
+  if (C <= 32 && !tuning().corr_disable_ring)
+    return vec ? launch_mma_ring_impl<MD, true>(d1, d2, out, N, C, H, W, obs, slope, st)
+               : launch_mma_ring_impl<MD, false>(d1, d2, out, N, C, H, W, obs, slope, st);
   return vec ? launch_mma_impl<MD, true>(d1, d2, out, N, C, H, W, obs, slope, st)
              : launch_mma_impl<MD, false>(d1, d2, out, N, C, H, W, obs, slope, st);
 }

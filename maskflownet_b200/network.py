@@ -94,7 +94,7 @@ class _FlowNetBase(nn.Module):
             if with_mask and lvl > 2:
                 setattr(self, f"pred_mask{lvl}", _conv(c, 1))
             if lvl > 2:
-                setattr(self, f"upfeat{lvl - 1}", nn.ConvTranspose2d(c, upfeat_ch[5 - lvl + 0] if False else upfeat_ch[6 - lvl - 1 + 0], 4, 2, 1))
+                setattr(self, f"upfeat{lvl - 1}", nn.ConvTranspose2d(c, upfeat_ch[6 - lvl], 4, 2, 1))
         c2 = in_ch[2] + sum(DECODER_CH)
         dil = (1, 2, 4, 8, 16, 1)
         chs = (128, 128, 128, 96, 64, 32)
@@ -115,6 +115,7 @@ class MaskFlownetS(_FlowNetBase):
         self.md = 4
         self.border_mode = border_mode
         self.upfeat_ch = tuple(upfeat_ch)
+        self.event_hook = None  # optional callable(kind, level, 0|1): bench.py brackets kernels with CUDA events
         cin = 3
         for lvl in range(1, 7):
             co = PYRAMID_CH[lvl]
@@ -133,7 +134,7 @@ class MaskFlownetS(_FlowNetBase):
         msra_prelu_init_(self)
 
     # one correlation + its consumers' concat buffer: [corr | extras...]
-    def _corr_block(self, f1, f2, extras: List[torch.Tensor]):
+    def _corr_block(self, lvl, f1, f2, extras: List[torch.Tensor]):
         N, _, H, W = f1.shape
         D = (2 * self.md + 1) ** 2
         if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
@@ -141,7 +142,12 @@ class MaskFlownetS(_FlowNetBase):
             return torch.cat([corr] + extras, dim=1) if extras else corr
         tot = D + sum(e.shape[1] for e in extras)
         buf = torch.empty((N, tot, H, W), device=f1.device, dtype=torch.float32)
+        hook = self.event_hook
+        if hook is not None:
+            hook("corr", lvl, 0)
         ops.correlation(f1, f2, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE, out=buf[:, :D])
+        if hook is not None:
+            hook("corr", lvl, 1)
         c = D
         for e in extras:
             buf[:, c:c + e.shape[1]].copy_(e)
@@ -153,7 +159,7 @@ class MaskFlownetS(_FlowNetBase):
         (network/MaskFlownet.py:302-315).  srcs (needed only by the cascade) is built when want_cascade_inputs."""
         c1 = self._pyramid(im1, "abc")
         c2 = self._pyramid(im2, "abc")
-        x = self._dense(6, self._corr_block(c1[5], c2[5], []))
+        x = self._dense(6, self._corr_block(6, c1[5], c2[5], []))
         flow = self.pred_flow6(x)
         mask = self.pred_mask6(x)
         flows = [flow]
@@ -161,9 +167,13 @@ class MaskFlownetS(_FlowNetBase):
             feat = tF.leaky_relu(getattr(self, f"upfeat{lvl}")(x), SLOPE)
             dp = getattr(self, f"deform{lvl}")
             trade = getattr(self, f"conv{lvl}f")(feat)
+            if self.event_hook is not None:
+                self.event_hook("warp", lvl, 0)
             warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, mask, dp.weight, dp.bias, trade, self.scale,
                                              float(STRIDES[lvl]), 2, SLOPE, self.border_mode)
-            x = self._dense(lvl, self._corr_block(c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up]))
+            if self.event_hook is not None:
+                self.event_hook("warp", lvl, 1)
+            x = self._dense(lvl, self._corr_block(lvl, c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up]))
             flow = flow_up + getattr(self, f"pred_flow{lvl}")(x)
             if lvl > 2:
                 mask = getattr(self, f"pred_mask{lvl}")(x)

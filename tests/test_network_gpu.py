@@ -1,0 +1,131 @@
+"""GPU tests of the product model graph: against the golden fixture from the reference's own graph, against the oracle
+network on fresh inputs, the cascade, a training step, and the reference model file running unchanged on the CUDA
+operators through the mx shim (when the reference tree is present)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from maskflownet_b200 import _lib, mx, network, ops  # noqa: E402
+from oracle import network_ref  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, G)
+from make_golden import named_init, seeded_images  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _named_model(cls=network.MaskFlownetS):
+    m = cls()
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            p.copy_(named_init(k.replace("MaskFlownet_S.", ""), p.shape) if cls is network.MaskFlownetS
+                    else named_init(k, p.shape))
+    return m.cuda().eval()
+
+
+def test_product_graph_matches_reference_graph_fixture():
+    d = np.load(os.path.join(G, "net_ref_graph.npz"))
+    model = _named_model()
+    im1, im2 = seeded_images()
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        preds, occ, srcs = model(im1.cuda(), im2.cuda(), want_cascade_inputs=True)
+    assert _lib.launch_count() - n0 == 5 + 4 + 1          # 5 correlations, 4 fused warps, 1 cascade-input kernel
+    for k, p in zip(("pred6", "pred5", "pred4", "pred3", "pred2"), preds):
+        err = np.abs(p.cpu().numpy() - d[k]).max()
+        assert err < 2e-3, (k, err)                       # flows reach ~12 px; 2e-3 px absolute = 1e-4 * scale
+    assert np.abs(occ[0].cpu().numpy() - d["occ"]).max() < 1e-4
+    assert np.abs(srcs[4].cpu().numpy() - d["c40"].astype(np.float32)).max() < 3e-3
+
+
+def test_product_graph_matches_oracle_network_batch2():
+    model = _named_model()
+    a1, a2 = seeded_images(seed=5, n=2, h=64, w=192)
+    params = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    with torch.no_grad():
+        preds = model(a1.cuda(), a2.cuda())[0]
+        ref = network_ref.maskflownet_s_forward(params, a1, a2, threads=8)[0]
+    for p, r in zip(preds, ref):
+        assert (p.cpu() - r).abs().max().item() < 2e-3
+
+
+def test_predict_flow_pipeline():
+    model = _named_model()
+    rng = np.random.default_rng(0)
+    u1 = torch.from_numpy(rng.integers(0, 256, (1, 3, 64, 128), dtype=np.uint8))
+    u2 = torch.from_numpy(rng.integers(0, 256, (1, 3, 64, 128), dtype=np.uint8))
+    flow = network.predict_flow(model, u1.cuda(), u2.cuda())
+    params = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    ref = network_ref.predict_flow(params, u1, u2, threads=8)
+    assert flow.shape == (1, 2, 64, 128)
+    assert (flow.cpu() - ref).abs().max().item() < 5e-3
+
+
+def test_cascade_forward_runs_and_uses_md2_kernels():
+    model = network.MaskFlownet().cuda().eval()
+    a1, a2 = seeded_images(seed=7, n=1, h=64, w=128)
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        preds, vis, _ = model(a1.cuda(), a2.cuda())
+    assert [tuple(p.shape) for p in preds] == [(1, 2, 1, 2), (1, 2, 2, 4), (1, 2, 4, 8), (1, 2, 8, 16), (1, 2, 16, 32)]
+    assert all(torch.isfinite(p).all() for p in preds)
+    assert _lib.launch_count() - n0 == 10 + 10 + 5   # S head (5 corr, 4 warp, 1 image warp) + cascade (10 corr, 5 warp)
+
+
+def test_training_step_gradients_flow_through_cuda_backward():
+    model = _named_model().train()
+    a1, a2 = seeded_images(seed=9, n=2, h=64, w=128)
+    preds = model(a1.cuda(), a2.cuda())[0]
+    loss = sum(w * p.square().mean() for w, p in zip((.005, .01, .02, .08, .32), preds))
+    loss.backward()
+    for name in ("deform5.weight", "deform2.bias", "conv2f.weight", "conv1a.weight", "pred_mask3.weight"):
+        g = dict(model.named_parameters())[name].grad
+        assert g is not None and torch.isfinite(g).all() and g.abs().max().item() > 0, name
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/network"), reason="reference tree not present on this box")
+def test_reference_file_runs_unchanged_on_cuda_operators():
+    ref = mx.load_reference_network("/root/reference")
+    from maskflownet_b200.mx import ndarray as F
+    net = ref.MaskFlownet_S(config=mx.Reader({}))
+    net.initialize(seed=0, device="cuda")
+    a1, a2 = seeded_images()
+    with torch.no_grad():
+        preds, occ, srcs = net(F.NDArray(a1.cuda()), F.NDArray(a2.cuda()))
+    assert preds[-1].shape == (1, 2, 16, 32)
+
+
+def test_shim_operator_call_style_on_cuda():
+    """The call style of network/MaskFlownet.py:195,230 and network/layer.py:17-18,119 through the F shim."""
+    from maskflownet_b200.mx import ndarray as F
+    from oracle import cref
+    rng = np.random.default_rng(1)
+    c1 = rng.standard_normal((1, 32, 8, 12)).astype(np.float32)
+    c2 = rng.standard_normal((1, 32, 8, 12)).astype(np.float32)
+    out = F.Correlation(F.NDArray(torch.from_numpy(c1).cuda()), F.NDArray(torch.from_numpy(c2).cuda()), pad_size=4,
+                        kernel_size=1, max_displacement=4, stride1=1, stride2=1, is_multiply=1)
+    assert np.abs(out.asnumpy() - cref.correlation_forward(c1, c2)).max() < 1e-4
+    flow = F.NDArray(torch.from_numpy((rng.standard_normal((1, 2, 8, 12)) * 0.2).astype(np.float32)).cuda())
+    w = (rng.standard_normal((32, 32, 3, 3)) * 0.1).astype(np.float32)
+    offs = F.repeat(F.expand_dims(flow * 20. / 8, axis=1), 9, axis=1).reshape((0, -3, -2))
+    warp = F.contrib.DeformableConvolution(F.NDArray(torch.from_numpy(c2).cuda()), offs,
+                                           F.NDArray(torch.from_numpy(w).cuda()), name='fwd', kernel=(3, 3),
+                                           stride=(1, 1), dilate=(1, 1), pad=(1, 1), num_filter=32, num_group=1,
+                                           no_bias=True, layout='NCHW', num_deformable_group=1)
+    assert np.abs(warp.asnumpy() - cref.deformable_conv_forward(c2, offs.asnumpy(), w, None)).max() < 1e-4
+    img = rng.standard_normal((1, 3, 8, 12)).astype(np.float32)
+    grid = F.GridGenerator(data=flow.flip(axis=1), transform_type="warp")
+    rec = F.BilinearSampler(F.NDArray(torch.from_numpy(img).cuda()), grid)
+    assert np.abs(rec.asnumpy() - cref.reconstruction2d(img, flow.asnumpy())).max() < 1e-4

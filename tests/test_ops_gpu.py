@@ -302,3 +302,21 @@ def test_native_launch_counter_moves():
     ops.correlation(a, a)
     assert _lib.launch_count() == n0 + 1
     assert "corr_mma_kernel" in _lib.last_kernel()
+
+
+@pytest.mark.parametrize("cap", [1, 3, 7, 148])
+@pytest.mark.parametrize("shape,md", [((2, 32, 45, 70), 4), ((3, 24, 31, 64), 2), ((2, 16, 27, 15), 4),
+                                      ((2, 64, 30, 40), 4), ((1, 100, 14, 36), 2)])
+def test_correlation_mma_long_tile_runs(shape, md, cap):
+    """Persistent-grid bookkeeping: with the grid capped, each CTA marches through many tiles (ring-slot recycling,
+    strip changes, barrier phase flips), and results must not depend on the grid size."""
+    rng = np.random.default_rng(21)
+    f1, f2 = feat(rng, shape), feat(rng, shape)
+    ref = cref.correlation_forward(f1, f2, pad_size=md, max_displacement=md, threads=8)
+    _lib.set_tuning("corr_grid_cap", cap)
+    try:
+        got = ops.correlation(cu(f1), cu(f2), pad_size=md, max_displacement=md, algo=ops.CORR_MMA_BF16X3)
+        got = got.cpu().numpy()
+    finally:
+        _lib.set_tuning("corr_grid_cap", 0)
+    assert np.abs(got - ref).max() <= 1e-4, _lib.last_kernel()

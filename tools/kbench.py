@@ -35,6 +35,9 @@ def timeit(fn, iters, flush):
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
+        # keep the GPU busy (~0.3 ms) while the CPU enqueues event + launch, so that the events bracket pure device
+        # time and not the Python/ctypes launch latency
+        torch.cuda._sleep(600_000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -54,6 +57,8 @@ def main():
     ap.add_argument("--n", type=int, default=8)
     ap.add_argument("--hw", default="448x1024")
     ap.add_argument("--md", type=int, default=4)
+    ap.add_argument("--levels", default="2,3,4,5,6")
+    ap.add_argument("--algos", default="simt,mma_bf16x3,generic")
     args = ap.parse_args()
     H0, W0 = map(int, args.hw.split("x"))
     N = args.n
@@ -72,7 +77,10 @@ def main():
         logf.flush()
 
     g = torch.Generator(device=dev).manual_seed(0)
+    lv = [int(v) for v in args.levels.split(",")]
     for L, C in sorted(LEVELS.items()):
+        if L not in lv:
+            continue
         H, W = H0 >> L, W0 >> L
         f1 = torch.nn.functional.leaky_relu(torch.randn(N, C, H, W, device=dev, generator=g), 0.1)
         f2 = torch.nn.functional.leaky_relu(torch.randn(N, C, H, W, device=dev, generator=g), 0.1)
@@ -84,7 +92,7 @@ def main():
             ref = None
             for name, algo in (("simt", ops.CORR_SIMT), ("mma_bf16x3", ops.CORR_MMA_BF16X3),
                                ("generic", ops.CORR_GENERIC)):
-                if algo == ops.CORR_GENERIC and L < 4:
+                if (algo == ops.CORR_GENERIC and L < 4) or name not in args.algos.split(","):
                     continue
                 out = torch.empty(N, D, H, W, device=dev)
                 fn = lambda: ops.correlation(f1, f2, pad_size=md, max_displacement=md, leaky_slope=0.1, algo=algo,
