@@ -301,7 +301,7 @@ def test_native_launch_counter_moves():
     n0 = _lib.launch_count()
     ops.correlation(a, a)
     assert _lib.launch_count() == n0 + 1
-    assert "corr_mma_kernel" in _lib.last_kernel()
+    assert "corr_mma" in _lib.last_kernel()
 
 
 @pytest.mark.parametrize("cap", [1, 3, 7, 148])
