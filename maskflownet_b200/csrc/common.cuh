@@ -16,6 +16,7 @@ void note_kernel(const char* name);
 struct Tuning {
   int corr_grid_cap = 0;      // > 0: cap the persistent grid of the MMA correlation kernels (tests force long tile runs)
   int corr_disable_ring = 0;  // 1: use the tile kernel even for C <= 32
+  int corr_dbg = 0;           // profiling aid for the ring kernel: 2 = producers idle, 4 = no epilogue, 8 = no MMA (results invalid)
 };
 Tuning& tuning();
 

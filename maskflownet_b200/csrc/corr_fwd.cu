@@ -426,255 +426,429 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1)
 }
 
 // =====================================================================================================
-// Tensor-core kernel, strip-marching variant for C <= 32 (one channel chunk): the dominant levels.
+// Tensor-core kernel, strip-marching variant for C <= 32 (one channel chunk): the dominant levels (v4).
 //
-// A CTA owns a contiguous run of tiles in (n, x-strip, y) order and marches down each strip.  The split bf16 rows
-// of data2 live in a ring of R row slots, so a tile that continues a strip loads only its TH new rows (the 2*MD
-// halo rows above are still resident), all of them in one batch of independent 16-byte loads per producer thread
-// (enough bytes in flight to cover HBM latency).  Three tiles are in flight: consumers on tile s, producers up to
-// tile s+2.  Consumers prefetch the data1 fragments of the next tile into registers before starting the MMAs of the
-// current one, and run the displacement rows in two passes to keep the accumulator footprint at 40 registers.
+// A CTA (16 symmetric warps, persistent, one per SM) owns a contiguous run of 8x32-pixel tiles in (n, x-strip, y) order
+// and marches down each strip.  Shared memory holds, in split-bf16 (hi | lo), pixel-major form with 64 B per pixel and
+// XOR-swizzled 16-byte chunks (conflict-free ldmatrix and STS without padding):
+//   * a ring of 24 data2 rows: the 16 halo rows of the current tile + the 8 new rows of the next one (a tile that
+//     continues a strip loads only its 8 new rows),
+//   * two stages of 8 data1 rows (pre-scaled by 1/C).
+// Software pipeline per tile, identical in every warp:
+//   1. issue the 16-byte global loads of the NEXT tile's rows into registers (5 octet-rows per warp: 80 KB in flight per SM)
+//   2. current tile: B fragments (data1) by ldmatrix; walk the halo rows: each ldmatrix'ed A row (16 data2 positions x
+//      16 channels, hi and lo) feeds the MMAs of both pixel rows of the warp's item (2 rows x 8 pixels): hi*lo + lo*hi +
+//      hi*hi into fp32 accumulators; dy in passes of 3; per pass the accumulators go through a small staging buffer
+//      (predicated STS with lane-constant predicates, 16-byte LDS, LeakyReLU, 16-byte coalesced STG)
+//   3. split / transpose the prefetched registers into the ring and the other data1 stage
+//   4. __syncthreads
+// so global-load latency hides behind a whole tile of tensor work and no warp ever spins on a barrier.
 // =====================================================================================================
-namespace tcr {
-using namespace tc;
-constexpr int R = TH + 2 * 4 + 2 * TH;  // 26 row slots: 14 (tile s) + 6 (tile s+1) + 6 (tile s+2)
-constexpr int NSTAGE = 3;
-constexpr int ROW_BYTES = HWP * RS;       // one split row (hi or lo): 40 px * 80 B
-constexpr int LO_OFF = R * ROW_BYTES;
-constexpr int PASS = 5;                   // displacement rows per accumulator pass
-__host__ __device__ constexpr int ring_smem_bytes(int md) {
-  return 2 * R * ROW_BYTES + NCONS * (2 * md + 1) * STG_STRIDE * 4 + 64;
-}
-}  // namespace tcr
+namespace r4 {
+using tc::ldsm_x4;
+using tc::mma_bf16;
+using tc::smem_u32;
+using tc::split_pair;
+constexpr int TH = 8, TW = 32, HX = 4, HWP = TW + 2 * HX;
+constexpr int NWARPS = 16, NTHREADS = 32 * NWARPS;
+constexpr int PXB = 64;                          // bytes per pixel (32 channels bf16), no padding
+constexpr int R = 24;                            // ring rows
+constexpr int ROW_BYTES = HWP * PXB;             // 2560: one split row (hi or lo)
+constexpr int RING_LO = R * ROW_BYTES;
+constexpr int RING_BYTES = 2 * RING_LO;
+constexpr int F1_ROW_BYTES = TW * PXB;           // 2048
+constexpr int F1_LO = TH * F1_ROW_BYTES;
+constexpr int F1_STAGE = 2 * F1_LO;              // hi + lo of one stage
+constexpr int PASS = 3;
+constexpr int SSTR = TW + 4;                     // staging row: the tile's 32 pixels + 4 pad (keeps float4 alignment)
+constexpr int UNITS_F1 = TH * 4;                 // load units (32 lanes x 8 channels) of the data1 rows
+constexpr int UPW = 5;                           // units per warp per batch: 32 + 6*8 = 80 = 16 warps x 5
+static_assert(UNITS_F1 + 6 * TH == UPW * NWARPS, "unit split of a continuing tile must be exact");
+__host__ __device__ constexpr int stg_group_bytes(int md) { return 2 * PASS * (2 * md + 1) * SSTR * 4; }  // 2 buffers
+__host__ __device__ constexpr int smem_bytes(int md) { return RING_BYTES + 2 * F1_STAGE + 4 * stg_group_bytes(md); }
+__device__ __forceinline__ int swz(int p, int c) { return p * PXB + ((c ^ ((p >> 1) & 3)) << 4); }
+}  // namespace r4
 
 template <int MD, bool VEC>
-__global__ void __launch_bounds__(tc::NTHREADS, 1)
+__global__ void __launch_bounds__(r4::NTHREADS, 1)
     corr_mma_ring_kernel(const float* __restrict__ d1, const float* __restrict__ d2, float* __restrict__ out,
                          int N, int C, int H, int W, long long out_bs, float slope, int tilesX, int tilesY,
-                         int numTiles) {
-  using namespace tcr;
+                         int numTiles, int ovec, int dbg) {
+  using namespace r4;
   constexpr int G = 2 * MD + 1;
-  constexpr int HR = TH + 2 * MD;   // halo rows of one tile
-  constexpr int NEWR = TH;          // rows a continuing tile has to load
+  constexpr int HR = TH + 2 * MD;
+  constexpr int NPASS = (G + PASS - 1) / PASS;
+  constexpr int SROWS = PASS * G;   // staging rows (= output planes) per pass
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;
-  float* stg_all = reinterpret_cast<float*>(smem_raw + 2 * R * ROW_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * R * ROW_BYTES + NCONS * G * STG_STRIDE * 4);
-  const uint32_t bar_full = smem_u32(bars);               // [NSTAGE]
-  const uint32_t bar_empty = smem_u32(bars + NSTAGE);     // [NSTAGE]
+  unsigned char* f1s = smem_raw + RING_BYTES;
 
+  if (dbg & 16) return;   // profiling aid: launch overhead only
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(bar_full + 8 * i, NPROD * 32);
-      mbar_init(bar_empty + 8 * i, NCONS);
+  // work assignment: a CTA owns one contiguous piece of one (n, x-strip) column of tiles -- numTiles here is the number
+  // of pieces per strip; strips are never changed mid-run, so only the prologue tile is "fresh"
+  const int ppS = numTiles;
+  const int strip = blockIdx.x / ppS, piece = blockIdx.x - strip * ppS;
+  const int ty_begin = (tilesY * piece) / ppS, ty_end = (tilesY * (piece + 1)) / ppS;
+  const int t_begin = strip * tilesY + ty_begin;
+  const int nStages = ty_end - ty_begin;
+  const size_t plane = (size_t)H * W;
+  const float invC = 1.f / (float)C;
+
+  struct TileGeo {
+    int n, x0, y0, first_slot, rr0, nrows;  // nrows = data2 halo rows to load (8 continuing, HR fresh), starting at rr0
+    bool fresh;
+  };
+  auto geo = [&](int s, int& wr) {
+    TileGeo t;
+    const int tile = t_begin + s;
+    const int ty = tile % tilesY, tx = (tile / tilesY) % tilesX;
+    t.n = tile / (tilesY * tilesX);
+    t.x0 = tx * TW;
+    t.y0 = ty * TH;
+    t.fresh = (s == 0);
+    (void)ty;
+    t.first_slot = t.fresh ? wr : (wr + R - 2 * MD) % R;
+    t.rr0 = t.fresh ? 0 : 2 * MD;
+    t.nrows = t.fresh ? HR : TH;
+    wr = (wr + t.nrows) % R;
+    return t;
+  };
+  // ---- load units: 32 lanes x 8 channels of one 16-byte smem chunk per pixel; every LDG touches full sectors of 1-4 lines.
+  //   ids [0, 32)                     data1 row id>>2, pixels x0..x0+31 (one 128-byte line per channel), chunk id&3
+  //   ids [32, 32+4*nrows)            data2 halo row (k>>2), pixels x0..x0+31, chunk k&3
+  //   ids [.., .. + 2*nrows)          data2 halo columns: 2 rows x (left octet | right octet), chunk k&3
+  struct UnitPos {
+    bool is1, active;  // data1 unit? / does this lane carry a pixel that is stored
+    int row;           // data1 tile row or data2 halo row
+    int chunk, pidx;   // 16-byte chunk (8 channels); pixel index inside the smem row
+    int y, x;          // image coordinates
+  };
+  auto unit_pos = [&](const TileGeo& t, int id) {
+    UnitPos u;
+    const int nmain = 4 * t.nrows;
+    u.active = id < UNITS_F1 + nmain + 2 * t.nrows;
+    u.is1 = id < UNITS_F1;
+    if (u.is1) {
+      u.row = id >> 2;
+      u.chunk = id & 3;
+      u.pidx = lane;
+      u.y = t.y0 + u.row;
+      u.x = t.x0 + lane;
+    } else if (id < UNITS_F1 + nmain) {
+      const int k = id - UNITS_F1;
+      u.row = t.rr0 + (k >> 2);
+      u.chunk = k & 3;
+      u.pidx = HX + lane;
+      u.y = t.y0 - MD + u.row;
+      u.x = t.x0 + lane;
+    } else {
+      const int k = id - UNITS_F1 - nmain;
+      const int blk = lane >> 3, px8 = lane & 7, side = blk & 1;
+      u.row = t.rr0 + 2 * (k >> 2) + (blk >> 1);
+      u.chunk = k & 3;
+      u.pidx = side ? TW + HX + px8 : px8 - HX;
+      u.x = side ? t.x0 + TW + px8 : t.x0 - 8 + px8;
+      u.y = t.y0 - MD + u.row;
+      u.active = u.active && (side ? px8 < HX : px8 >= HX);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    return u;
+  };
+  auto load_unit = [&](const TileGeo& t, int id, float (&e)[8]) {
+    const UnitPos u = unit_pos(t, id);
+    const bool ok = u.active && u.y >= 0 && u.y < H && u.x >= 0 && u.x < W;
+    const int c0 = 8 * u.chunk;
+    const float* p = (u.is1 ? d1 : d2) + ((size_t)t.n * C + c0) * plane + (size_t)u.y * W + u.x;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) e[c] = (ok && c0 + c < C) ? __ldg(p + (size_t)c * plane) : 0.f;
+  };
+  auto store_unit = [&](const TileGeo& t, int id, int f1stage, const float (&e)[8]) {
+    const UnitPos u = unit_pos(t, id);
+    if (!u.active) return;
+    unsigned char* rowp;
+    int lo_off;
+    float sc;
+    if (u.is1) {
+      rowp = f1s + f1stage * F1_STAGE + u.row * F1_ROW_BYTES;
+      lo_off = F1_LO;
+      sc = invC;
+    } else {
+      int slot = t.first_slot + u.row;
+      slot = slot >= 2 * R ? slot - 2 * R : (slot >= R ? slot - R : slot);
+      rowp = ring + slot * ROW_BYTES;
+      lo_off = RING_LO;
+      sc = 1.f;
+    }
+    uint4 hi, lo;
+    split_pair(e[0] * sc, e[1] * sc, hi.x, lo.x);
+    split_pair(e[2] * sc, e[3] * sc, hi.y, lo.y);
+    split_pair(e[4] * sc, e[5] * sc, hi.z, lo.z);
+    split_pair(e[6] * sc, e[7] * sc, hi.w, lo.w);
+    unsigned char* dst = rowp + swz(u.pidx, u.chunk);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+  };
+
+  // ---- consumer-side lane constants: item = pixel rows 2rp, 2rp+1 x pixels 8oc..8oc+7 of the tile ----
+  const int rp = warp >> 2, oc = warp & 3;
+  const int g = lane >> 2, j = lane & 3;
+  const int l8 = lane & 7, mi = lane >> 3;
+  const int sw = (l8 >> 1) & 3;   // swizzle term of this lane's ldmatrix rows (pixel index = multiple of 8 + l8)
+  const uint32_t ring_u32 = smem_u32(ring), f1_u32 = smem_u32(f1s);
+  // A (ring): matrices (8-row block mi&1, k-half mi>>1) -> a0..a3;  B (data1 stage): matrices (hi|lo = mi>>1, k-half mi&1)
+  uint32_t offA[2], offB[2];
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    offA[kk] = (uint32_t)((8 * oc + 8 * (mi & 1) + l8) * PXB + (((2 * kk + (mi >> 1)) ^ sw) << 4));
+    offB[kk] = (uint32_t)((8 * oc + l8) * PXB + (((2 * kk + (mi & 1)) ^ sw) << 4) + (mi >> 1) * F1_LO);
+  }
+  // accumulator element i of this lane: (row, col) = (g + 8*(i>>1), 2j + (i&1));  dx index = row - col - 4 + MD
+  bool okv[4];
+  int sto[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int dxi = g + 8 * (i >> 1) - 2 * j - (i & 1) - 4 + MD;
+    okv[i] = dxi >= 0 && dxi < G;
+    sto[i] = dxi * SSTR + 8 * oc + 2 * j + (i & 1);
+  }
+  // the four warps of a row pair share a staging area (two buffers: one per pixel row) and a named barrier
+  float* stg_g = reinterpret_cast<float*>(smem_raw + RING_BYTES + 2 * F1_STAGE) + rp * (2 * SROWS * SSTR);
+  const int tig = threadIdx.x & 127;  // thread index inside the row-pair group
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + rp) : "memory"); };
+
+  // ---- steady-state load roles (a continuing tile = 80 units): every warp takes two data1 units (row w>>1, 16 channels),
+  //      two data2 units (new row w>>1, 16 channels) and one halo-column unit (row pair w>>2, chunk w&3): addresses are a
+  //      base pointer + k*plane, shared-memory offsets are lane constants ----
+  const int lr = warp >> 1, lc = 2 * (warp & 1);
+  const int hrp2 = 2 * (warp >> 2), hch = warp & 3;
+  const int hblk = lane >> 3, hpx8 = lane & 7, hside = hblk & 1;
+  const bool hact = hside ? hpx8 < HX : hpx8 >= HX;
+  const int hdx = hside ? TW + hpx8 : hpx8 - 8;
+  const int hrow = 2 * MD + hrp2 + (hblk >> 1);                 // halo row of this lane's halo-column pixel
+  const uint32_t so_f1a = (uint32_t)(lr * F1_ROW_BYTES + swz(lane, lc)), so_f1b = (uint32_t)(lr * F1_ROW_BYTES + swz(lane, lc + 1));
+  const uint32_t so_ma = (uint32_t)swz(HX + lane, lc), so_mb = (uint32_t)swz(HX + lane, lc + 1);
+  const uint32_t so_h = (uint32_t)swz(hside ? TW + HX + hpx8 : hpx8 - HX, hch);
+  const bool fullC = (C == 32);      // no per-channel predicates needed
+  const size_t plane4 = plane;       // element stride between channel planes
+  auto prefetch_next = [&](const TileGeo& t, float (&e1)[16], float (&e2)[16], float (&eh)[8]) {
+    // running pointers (p += plane) instead of per-load 64-bit multiplies
+    const size_t nbase = (size_t)t.n * C;
+    {
+      const int y = t.y0 + lr, x = t.x0 + lane;
+      const bool ok = y < H && x < W;
+      const float* p = d1 + (nbase + 8 * lc) * plane + (size_t)y * W + x;
+      if (fullC) {
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { e1[c] = __ldg(p); p += plane4; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) e1[c] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { e1[c] = (ok && 8 * lc + c < C) ? __ldg(p) : 0.f; p += plane4; }
+      }
+    }
+    {
+      const int y = t.y0 + MD + lr, x = t.x0 + lane;   // halo row 2*MD + lr
+      const bool ok = y < H && x < W;
+      const float* p = d2 + (nbase + 8 * lc) * plane + (size_t)y * W + x;
+      if (fullC) {
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { e2[c] = __ldg(p); p += plane4; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) e2[c] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { e2[c] = (ok && 8 * lc + c < C) ? __ldg(p) : 0.f; p += plane4; }
+      }
+    }
+    {
+      const int y = t.y0 - MD + hrow, x = t.x0 + hdx;
+      const bool ok = hact && y < H && x >= 0 && x < W;
+      const float* p = d2 + (nbase + 8 * hch) * plane + (size_t)y * W + x;
+      if (fullC) {
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { eh[c] = __ldg(p); p += plane4; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) eh[c] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { eh[c] = (ok && 8 * hch + c < C) ? __ldg(p) : 0.f; p += plane4; }
+      }
+    }
+  };
+  auto put_chunk = [&](unsigned char* dst, int lo_off, const float* e, float sc) {
+    uint4 hi, lo;
+    split_pair(e[0] * sc, e[1] * sc, hi.x, lo.x);
+    split_pair(e[2] * sc, e[3] * sc, hi.y, lo.y);
+    split_pair(e[4] * sc, e[5] * sc, hi.z, lo.z);
+    split_pair(e[6] * sc, e[7] * sc, hi.w, lo.w);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+  };
+  auto store_next = [&](const TileGeo& t, int f1stage, const float (&e1)[16], const float (&e2)[16], const float (&eh)[8]) {
+    unsigned char* f1p = f1s + f1stage * F1_STAGE;
+    put_chunk(f1p + so_f1a, F1_LO, &e1[0], invC);
+    put_chunk(f1p + so_f1b, F1_LO, &e1[8], invC);
+    int slot = t.first_slot + 2 * MD + lr;
+    slot = slot >= 2 * R ? slot - 2 * R : (slot >= R ? slot - R : slot);
+    unsigned char* rp2 = ring + slot * ROW_BYTES;
+    put_chunk(rp2 + so_ma, RING_LO, &e2[0], 1.f);
+    put_chunk(rp2 + so_mb, RING_LO, &e2[8], 1.f);
+    if (hact) {
+      int hs = t.first_slot + hrow;
+      hs = hs >= 2 * R ? hs - 2 * R : (hs >= R ? hs - R : hs);
+      put_chunk(ring + hs * ROW_BYTES + so_h, RING_LO, &eh[0], 1.f);
+    }
+  };
+
+  // ---- prologue: bring in tile 0 completely ----
+  int wr = 0;
+  TileGeo cur = geo(0, wr);
+  {
+    constexpr int UPRO = (UNITS_F1 + 6 * HR + NWARPS - 1) / NWARPS;   // 8: the whole fresh tile in one batch of loads
+    float e[UPRO][8];
+    if (!(dbg & 32)) {
+#pragma unroll
+      for (int k = 0; k < UPRO; ++k) load_unit(cur, warp * UPRO + k, e[k]);
+#pragma unroll
+      for (int k = 0; k < UPRO; ++k) store_unit(cur, warp * UPRO + k, 0, e[k]);
+    }
   }
   __syncthreads();
 
-  // balanced contiguous tile range of this CTA; linear order = ((n * tilesX + tx) * tilesY + ty)
-  const int t_begin = (int)(((long long)numTiles * blockIdx.x) / gridDim.x);
-  const int t_end = (int)(((long long)numTiles * (blockIdx.x + 1)) / gridDim.x);
-  const int nStages = t_end - t_begin;
-  const size_t plane = (size_t)H * W;
-
-  if (warp >= NCONS) {
-    // ================================ PRODUCERS ================================
-    const int pw = warp - NCONS;
-    const int m = lane >> 4, j = lane & 15;
-    const int ca = 2 * j;
-    const bool c_ok0 = ca < C, c_ok1 = ca + 1 < C;
-    int wr = 0;  // next free ring slot
-    for (int s = 0; s < nStages; ++s) {
-      const int tile = t_begin + s;
-      const int ty = tile % tilesY, tx = (tile / tilesY) % tilesX, n = tile / (tilesY * tilesX);
-      const int x0 = tx * TW, y0 = ty * TH;
-      const bool fresh = (s == 0) || (ty == 0);
-      // ring slots are recycled from tile s-3; a fresh strip additionally needs s-1 and s-2 drained
-      if (s >= 3) mbar_wait(bar_empty + 8 * ((s - 3) % NSTAGE), ((s - 3) / NSTAGE) & 1);
-      if (fresh) {
-        if (s >= 2) mbar_wait(bar_empty + 8 * ((s - 2) % NSTAGE), ((s - 2) / NSTAGE) & 1);
-        if (s >= 1) mbar_wait(bar_empty + 8 * ((s - 1) % NSTAGE), ((s - 1) / NSTAGE) & 1);
-      }
-      const int first_slot = fresh ? wr : (wr + R - 2 * MD) % R;
-      const int rr0 = fresh ? 0 : 2 * MD;           // first halo row to load
-      const int nrows = fresh ? HR : NEWR;
-      wr = (wr + nrows) % R;
-      const float* pc = d2 + ((size_t)n * C + ca) * plane;
-      const int NOR = nrows * OCT_PER_ROW;
-      constexpr int U = (NEWR * OCT_PER_ROW + NPROD - 1) / NPROD;  // 9: a continuing tile is one batch
-      for (int o0 = pw; o0 < NOR; o0 += NPROD * U) {
-        float4 v0[U], v1[U];
-#pragma unroll
-        for (int uu = 0; uu < U; ++uu) {
-          const int o = o0 + uu * NPROD;
-          v0[uu] = make_float4(0.f, 0.f, 0.f, 0.f);
-          v1[uu] = v0[uu];
-          const int rr = rr0 + o / OCT_PER_ROW;
-          const int oct = o % OCT_PER_ROW;
-          const int pxr = 8 * oct + 4 * m - HX;
-          const int y = y0 - MD + rr;
-          const int x = x0 - 8 + 8 * oct + 4 * m;
-          if (o < NOR && pxr >= 0 && pxr < HWP && y >= 0 && y < H) {
-            const float* p = pc + (size_t)y * W + x;
-            if (VEC) {
-              if (x >= 0 && x < W) {
-                if (c_ok0) v0[uu] = __ldg(reinterpret_cast<const float4*>(p));
-                if (c_ok1) v1[uu] = __ldg(reinterpret_cast<const float4*>(p + plane));
-              }
-            } else {
-              float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (x + e >= 0 && x + e < W) {
-                  if (c_ok0) t0[e] = __ldg(p + e);
-                  if (c_ok1) t1[e] = __ldg(p + plane + e);
-                }
-              v0[uu] = make_float4(t0[0], t0[1], t0[2], t0[3]);
-              v1[uu] = make_float4(t1[0], t1[1], t1[2], t1[3]);
-            }
-          }
-        }
-#pragma unroll
-        for (int uu = 0; uu < U; ++uu) {
-          const int o = o0 + uu * NPROD;
-          const int rr = rr0 + o / OCT_PER_ROW;
-          const int oct = o % OCT_PER_ROW;
-          const int pxr = 8 * oct + 4 * m - HX;
-          if (o < NOR && pxr >= 0 && pxr < HWP) {
-            const int slot = (first_slot + rr) % R;
-            unsigned char* dst = ring + (size_t)slot * ROW_BYTES + pxr * RS + 4 * j;
-            const float a[4] = {v0[uu].x, v0[uu].y, v0[uu].z, v0[uu].w};
-            const float c[4] = {v1[uu].x, v1[uu].y, v1[uu].z, v1[uu].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              uint32_t hi, lo;
-              split_pair(a[e], c[e], hi, lo);
-              *reinterpret_cast<uint32_t*>(dst + e * RS) = hi;
-              *reinterpret_cast<uint32_t*>(dst + e * RS + LO_OFF) = lo;
-            }
-          }
-        }
-      }
-      mbar_arrive(bar_full + 8 * (s % NSTAGE));
+  for (int s = 0; s < nStages; ++s) {
+    // ---- 1. prefetch the next tile's rows into registers (40 independent 4-byte loads per thread) ----
+    const bool has_next = s + 1 < nStages;
+    TileGeo nxt = cur;
+    float pe1[16], pe2[16], peh[8];
+    if (has_next) {
+      nxt = geo(s + 1, wr);   // always a continuing tile: its 8 new rows go to the 8 ring slots the current tile does not use
+      if (!(dbg & 2)) prefetch_next(nxt, pe1, pe2, peh);
     }
-  } else {
-    // ================================ CONSUMERS ================================
-    const int r = warp >> 1;
-    const int xs = (warp & 1) * 16;
-    const int g = lane >> 2, j = lane & 3;
-    float* stg = stg_all + warp * (G * STG_STRIDE);
-    const float invC = 1.f / (float)C;
-    const int l8 = lane & 7, mi = lane >> 3;
-    const uint32_t off12 = (uint32_t)((xs + 8 * (mi & 1) + l8) * RS + 16 * (mi >> 1));
-    const uint32_t off3 = (uint32_t)((xs + 16 + l8) * RS + 16 * (mi & 1) + (mi >> 1) * LO_OFF);
-    const uint32_t ring_u32 = smem_u32(ring);
+
+    // ---- 2. current tile ----
+    uint32_t bq[2][2][4];   // [pixel row][kk] -> {hi k-half 0, hi k-half 1, lo k-half 0, lo k-half 1}
+#pragma unroll
+    for (int rw = 0; rw < 2; ++rw)
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+        ldsm_x4(f1_u32 + (uint32_t)((s & 1) * F1_STAGE + (2 * rp + rw) * F1_ROW_BYTES) + offB[kk], bq[rw][kk]);
+    const int yA = cur.y0 + 2 * rp;
+    float* obase = out + (size_t)cur.n * out_bs + (size_t)yA * W + cur.x0;
     const bool two_k = C > 16;
 
-    // raw data1 values of the NEXT tile (prefetched): [k-step][tile][e0,e1,e8,e9]
-    float raw[2][2][4];
-    auto load_raw = [&](int tile) {
-      const int ty = tile % tilesY, tx = (tile / tilesY) % tilesX, n = tile / (tilesY * tilesX);
-      const int y = ty * TH + r;
-      const float* f1n = d1 + (size_t)n * C * plane;
+#pragma unroll 1
+    for (int ps = 0; ps < NPASS; ++ps) {
+      const int d0 = ps * PASS;
+      float acc[2][PASS][4];
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk)
+      for (int rw = 0; rw < 2; ++rw)
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int x = tx * TW + xs + 8 * t + g;
-          const int c = 16 * kk + 2 * j;
-          const bool ok = (y < H) && (x < W);
-          const float* p = f1n + (size_t)c * plane + (size_t)y * W + x;
-          raw[kk][t][0] = (ok && c < C) ? __ldg(p) : 0.f;
-          raw[kk][t][1] = (ok && c + 1 < C) ? __ldg(p + plane) : 0.f;
-          raw[kk][t][2] = (ok && c + 8 < C) ? __ldg(p + 8 * plane) : 0.f;
-          raw[kk][t][3] = (ok && c + 9 < C) ? __ldg(p + 9 * plane) : 0.f;
-        }
-    };
-    if (nStages > 0) load_raw(t_begin);
-
-    int wr = 0;
-    for (int s = 0; s < nStages; ++s) {
-      const int tile = t_begin + s;
-      const int ty = tile % tilesY, tx = (tile / tilesY) % tilesX, n = tile / (tilesY * tilesX);
-      const int x0 = tx * TW, y0 = ty * TH;
-      const int y = y0 + r;
-      const bool fresh = (s == 0) || (ty == 0);
-      const int first_slot = fresh ? wr : (wr + R - 2 * MD) % R;
-      wr = (wr + (fresh ? HR : NEWR)) % R;
-
-      uint32_t bh[2][2][2], bl[2][2][2];
+        for (int dd = 0; dd < PASS; ++dd)
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk)
+          for (int i = 0; i < 4; ++i) acc[rw][dd][i] = 0.f;
+      if (!(dbg & 8)) {
+        // flat list of (kk, hh) steps; the fragments of step i+1 are fetched before the MMAs of step i are issued
+        constexpr int NST = 2 * (PASS + 1);
+        uint32_t ah[2][4], al[2][4];
+        auto frag = [&](int st, uint32_t (&fh)[4], uint32_t (&fl)[4]) {
+          const int kk = st / (PASS + 1), hh = st % (PASS + 1);
+          int slot = cur.first_slot + 2 * rp + d0 + hh;
+          slot = slot >= 2 * R ? slot - 2 * R : (slot >= R ? slot - R : slot);
+          const uint32_t rowoff = ring_u32 + (uint32_t)(slot * ROW_BYTES) + offA[kk];
+          ldsm_x4(rowoff, fh);
+          ldsm_x4(rowoff + RING_LO, fl);
+        };
+        frag(0, ah[0], al[0]);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          split_pair(raw[kk][t][0], raw[kk][t][1], bh[kk][t][0], bl[kk][t][0]);
-          split_pair(raw[kk][t][2], raw[kk][t][3], bh[kk][t][1], bl[kk][t][1]);
-        }
-      if (s + 1 < nStages) load_raw(tile + 1);  // in flight during this tile's MMAs
-
-      mbar_wait(bar_full + 8 * (s % NSTAGE), (s / NSTAGE) & 1);
-      float* obase = out + (size_t)n * out_bs + (size_t)y * W + (x0 + xs);
-      const int p = lane & 15, hsel = lane >> 4;
-      const int base_slot = first_slot + r;
-
-#pragma unroll
-      for (int d0 = 0; d0 < G; d0 += PASS) {
-        float acc[PASS][2][4];
-#pragma unroll
-        for (int d = 0; d < PASS; ++d)
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[d][t][i] = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
+        for (int st = 0; st < NST; ++st) {
+          const int kk = st / (PASS + 1), hh = st % (PASS + 1);
           if (kk == 1 && !two_k) break;
-#pragma unroll
-          for (int d = 0; d < PASS; ++d) {
-            if (d0 + d >= G) break;
-            int slot = base_slot + d0 + d;
-            if (slot >= R) slot -= R;
-            const uint32_t rowoff = ring_u32 + (uint32_t)(slot * ROW_BYTES + 32 * kk);
-            uint32_t h[4], l[4], x3[4];
-            ldsm_x4(rowoff + off12, h);
-            ldsm_x4(rowoff + off12 + LO_OFF, l);
-            ldsm_x4(rowoff + off3, x3);
-            mma_bf16(acc[d][0], h[0], h[1], h[2], h[3], bl[kk][0][0], bl[kk][0][1]);
-            mma_bf16(acc[d][0], l[0], l[1], l[2], l[3], bh[kk][0][0], bh[kk][0][1]);
-            mma_bf16(acc[d][0], h[0], h[1], h[2], h[3], bh[kk][0][0], bh[kk][0][1]);
-            mma_bf16(acc[d][1], h[1], x3[0], h[3], x3[1], bl[kk][1][0], bl[kk][1][1]);
-            mma_bf16(acc[d][1], l[1], x3[2], l[3], x3[3], bh[kk][1][0], bh[kk][1][1]);
-            mma_bf16(acc[d][1], h[1], x3[0], h[3], x3[1], bh[kk][1][0], bh[kk][1][1]);
+          if (st + 1 < NST) frag(st + 1, ah[(st + 1) & 1], al[(st + 1) & 1]);
+          // halo row 2rp + d0 + hh serves (pixel row 0, dd = hh) and (pixel row 1, dd = hh-1)
+          const bool useA = hh < PASS && d0 + hh < G;
+          const bool useB = hh >= 1 && d0 + hh - 1 < G;
+          uint32_t(&fh)[4] = ah[st & 1];
+          uint32_t(&fl)[4] = al[st & 1];
+          if (useA) {
+            float(&a)[4] = acc[0][hh < PASS ? hh : 0];
+            mma_bf16(a, fh[0], fh[1], fh[2], fh[3], bq[0][kk][2], bq[0][kk][3]);
+            mma_bf16(a, fl[0], fl[1], fl[2], fl[3], bq[0][kk][0], bq[0][kk][1]);
+            mma_bf16(a, fh[0], fh[1], fh[2], fh[3], bq[0][kk][0], bq[0][kk][1]);
           }
-        }
-        if (d0 + PASS >= G) {  // last pass: every shared-memory read of this tile is done
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_empty + 8 * (s % NSTAGE));
-        }
-#pragma unroll
-        for (int d = 0; d < PASS; ++d) {
-          if (d0 + d >= G) break;
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = g + 8 * (i >> 1), col = 2 * j + (i & 1);
-              const int dxi = row - col - 4 + MD;
-              if (dxi >= 0 && dxi < G) stg[dxi * STG_STRIDE + 8 * t + col] = leaky(acc[d][t][i] * invC, slope);
-            }
-          __syncwarp();
-          if (y < H && x0 + xs + p < W) {
-#pragma unroll
-            for (int dxi = hsel; dxi < G; dxi += 2)
-              obase[(size_t)((d0 + d) * G + dxi) * plane + p] = stg[dxi * STG_STRIDE + p];
+          if (useB) {
+            float(&a)[4] = acc[1][hh >= 1 ? hh - 1 : 0];
+            mma_bf16(a, fh[0], fh[1], fh[2], fh[3], bq[1][kk][2], bq[1][kk][3]);
+            mma_bf16(a, fl[0], fl[1], fl[2], fl[3], bq[1][kk][0], bq[1][kk][1]);
+            mma_bf16(a, fh[0], fh[1], fh[2], fh[3], bq[1][kk][0], bq[1][kk][1]);
           }
-          __syncwarp();
         }
       }
+      if (dbg & 4) continue;
+      // ---- epilogue of this pass (cooperative across the 4 warps of the row pair): each warp drops its 8-pixel band
+      //      pieces into the group's [plane][32 px] staging buffer; then the 128 threads store full 128-byte plane rows ----
+      const int nrow = (G - d0 < PASS ? G - d0 : PASS) * G;   // planes of this pass
+#pragma unroll
+      for (int rw = 0; rw < 2; ++rw) {
+        float* sb = stg_g + rw * (SROWS * SSTR);
+#pragma unroll
+        for (int dd = 0; dd < PASS; ++dd) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (okv[i]) sb[dd * G * SSTR + sto[i]] = acc[rw][dd][i];
+        }
+      }
+      group_sync();
+#pragma unroll
+      for (int rw = 0; rw < 2; ++rw) {
+        const float* sb = stg_g + rw * (SROWS * SSTR);
+        const int y = yA + rw;
+        if (y < H) {
+          float* orow = obase + (size_t)rw * W + (size_t)(d0 * G) * plane;
+#pragma unroll
+          for (int k = 0; k < (SROWS * 8 + 127) / 128; ++k) {
+            const int idx = tig + 128 * k;
+            const int rowi = idx >> 3, quad = idx & 7;
+            const int xq = cur.x0 + 4 * quad;
+            if (rowi < nrow && xq < W) {
+              float4 v = *reinterpret_cast<const float4*>(sb + rowi * SSTR + 4 * quad);
+              if (slope <= 1.f) {
+                v.x = fmaxf(v.x, v.x * slope); v.y = fmaxf(v.y, v.y * slope);
+                v.z = fmaxf(v.z, v.z * slope); v.w = fmaxf(v.w, v.w * slope);
+              } else {
+                v.x = fminf(v.x, v.x * slope); v.y = fminf(v.y, v.y * slope);
+                v.z = fminf(v.z, v.z * slope); v.w = fminf(v.w, v.w * slope);
+              }
+              float* op = orow + (size_t)rowi * plane + 4 * quad;
+              if (ovec) {
+                *reinterpret_cast<float4*>(op) = v;
+              } else {
+                op[0] = v.x;
+                if (xq + 1 < W) op[1] = v.y;
+                if (xq + 2 < W) op[2] = v.z;
+                if (xq + 3 < W) op[3] = v.w;
+              }
+            }
+          }
+        }
+      }
+      group_sync();   // staging buffers are free again
     }
+
+    // ---- 3. split / transpose the prefetched rows (a fresh strip is fetched here, after everybody left the ring) ----
+    if (has_next && !(dbg & 2)) store_next(nxt, (s + 1) & 1, pe1, pe2, peh);
+    cur = nxt;
+    __syncthreads();
   }
 }
 
@@ -734,20 +908,28 @@ static int launch_mma_impl(const float* d1, const float* d2, float* out, int N, 
 template <int MD, bool VEC>
 static int launch_mma_ring_impl(const float* d1, const float* d2, float* out, int N, int C, int H, int W,
                                 long long obs, float slope, cudaStream_t st) {
-  using namespace tcr;
+  using namespace r4;
   const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
   const long long tiles = (long long)N * tilesX * tilesY;
-  const int smem = ring_smem_bytes(MD);
+  const int smem = r4::smem_bytes(MD);
+  const int ovec = ((W % 4) == 0 && (obs % 4) == 0 && aligned(out, 16)) ? 1 : 0;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(corr_mma_ring_kernel<MD, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_mma_ring_kernel): %s", cudaGetErrorString(e));
     attr_done = true;
   }
+  // strip-aligned work pieces: T = tiles per CTA if all SMs were used; each (n, x-strip) column is cut into
+  // ceil(tilesY / T) pieces, one CTA per piece (e.g. level 2 of configs[1]: 64 strips x 2 pieces of 7 tiles = 128 CTAs)
   const int cap = tuning().corr_grid_cap > 0 ? tuning().corr_grid_cap : kNumSMs;
-  const int grid = (int)(tiles < cap ? tiles : cap);
-  corr_mma_ring_kernel<MD, VEC><<<grid, NTHREADS, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope, tilesX, tilesY,
-                                                              (int)tiles);
+  const long long strips = (long long)N * tilesX;
+  const int T = (int)((tiles + cap - 1) / cap);
+  int pps = (tilesY + T - 1) / T;
+  if (pps < 1) pps = 1;
+  if (pps > tilesY) pps = tilesY;
+  const unsigned grid = (unsigned)(strips * pps);
+  corr_mma_ring_kernel<MD, VEC><<<grid, NTHREADS, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope, tilesX, tilesY, pps,
+                                                              ovec, tuning().corr_dbg);
   return check_launch(MD == 4 ? (VEC ? "corr_mma_ring_kernel<4,vec>" : "corr_mma_ring_kernel<4,scalar>")
                               : (VEC ? "corr_mma_ring_kernel<2,vec>" : "corr_mma_ring_kernel<2,scalar>"));
 }
@@ -755,7 +937,7 @@ static int launch_mma_ring_impl(const float* d1, const float* d2, float* out, in
 template <int MD>
 static int launch_mma(const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,
                       float slope, cudaStream_t st) {
-  const bool vec = (W % 4 == 0) && aligned(d2, 16);
+  const bool vec = (W % 4 == 0) && aligned(d2, 16) && aligned(d1, 16);
   if (C <= 32 && !tuning().corr_disable_ring)
     return vec ? launch_mma_ring_impl<MD, true>(d1, d2, out, N, C, H, W, obs, slope, st)
                : launch_mma_ring_impl<MD, false>(d1, d2, out, N, C, H, W, obs, slope, st);
