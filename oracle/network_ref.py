@@ -27,7 +27,7 @@ def _t(a):
 
 
 def maskflownet_s_forward(params: Dict[str, torch.Tensor], im1: torch.Tensor, im2: torch.Tensor, scale: float = 20.0,
-                          threads: int = 1, border_mode: int = 0, want_cascade_inputs: bool = False):
+                          threads: int = 1, border_mode: int = 0, want_cascade_inputs: bool = False, taps=None):
     """params: name -> CPU float tensor; im1, im2: (N,3,H,W) CPU float tensors (already /255 and centralised).
     Returns (predictions[5], [sigmoid(mask2)], c40 or None), numpy-free torch tensors on CPU."""
     P = {k: v.detach().cpu().float() for k, v in params.items()}
@@ -71,9 +71,12 @@ def maskflownet_s_forward(params: Dict[str, torch.Tensor], im1: torch.Tensor, im
         warp = _t(cref.deformable_conv_forward(c2[lvl - 1].numpy(), off.numpy(), P[f"deform{lvl}.weight"].numpy(),
                                                None if b is None else b.numpy(), border_mode=border_mode,
                                                threads=threads))
-        warp = warp * torch.sigmoid(mask_up) + conv(f"conv{lvl}f", feat, act=False)
-        warp = tF.leaky_relu(warp, SLOPE)
-        x = dense(lvl, torch.cat([corr(c1[lvl - 1], warp), c1[lvl - 1], feat, flow_up], dim=1))
+        trade = conv(f"conv{lvl}f", feat, act=False)
+        warp = tF.leaky_relu(warp * torch.sigmoid(mask_up) + trade, SLOPE)
+        cv = corr(c1[lvl - 1], warp)
+        if taps is not None:  # intermediate tensors of this level (fixtures with realistic value distributions)
+            taps[lvl] = dict(c1=c1[lvl - 1], c2=c2[lvl - 1], flow_c=flow, mask_c=mask, tradeoff=trade, warp=warp, corr=cv)
+        x = dense(lvl, torch.cat([cv, c1[lvl - 1], feat, flow_up], dim=1))
         flow = flow_up + conv(f"pred_flow{lvl}", x, act=False)
         if lvl > 2:
             mask = conv(f"pred_mask{lvl}", x, act=False)

@@ -129,3 +129,22 @@ def test_shim_operator_call_style_on_cuda():
     grid = F.GridGenerator(data=flow.flip(axis=1), transform_type="warp")
     rec = F.BilinearSampler(F.NDArray(torch.from_numpy(img).cuda()), grid)
     assert np.abs(rec.asnumpy() - cref.reconstruction2d(img, flow.asnumpy())).max() < 1e-4
+
+
+def test_multiscale_epe_loss_matches_oracle_and_backprops():
+    from maskflownet_b200 import losses
+    from oracle import torch_ref
+    rng = np.random.default_rng(3)
+    H, W = 64, 128
+    preds_np = [rng.standard_normal((2, 2, H // s, W // s)).astype(np.float32) for s in losses.SCALES]
+    flow = rng.standard_normal((2, 2, H, W)).astype(np.float32)
+    mask = (rng.random((2, 1, H, W)) > 0.3).astype(np.float32)
+    gp = [torch.from_numpy(p).cuda().requires_grad_() for p in preds_np]
+    rp = [torch.from_numpy(p).clone().requires_grad_() for p in preds_np]
+    lg = losses.multiscale_epe(torch.from_numpy(flow).cuda(), torch.from_numpy(mask).cuda(), gp)
+    lr = losses.multiscale_epe(torch.from_numpy(flow), torch.from_numpy(mask), rp, upsample=torch_ref.upsample)
+    assert (lg.cpu() - lr).abs().max().item() < 1e-5
+    lg.sum().backward()
+    lr.sum().backward()
+    for a, b in zip(gp, rp):
+        assert (a.grad.cpu() - b.grad).abs().max().item() < 1e-6

@@ -320,3 +320,18 @@ def test_correlation_mma_long_tile_runs(shape, md, cap):
     finally:
         _lib.set_tuning("corr_grid_cap", 0)
     assert np.abs(got - ref).max() <= 1e-4, _lib.last_kernel()
+
+
+def test_real_checkpoint_distribution_level2():
+    """Kernels on tensors with the value distribution of the shipped, trained checkpoint (fixture generated here from
+    weights/dbbSep30-1206_1000000.params by tests/golden/make_golden.py): fused warp and tensor-core correlation."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_weights_level2.npz"))
+    warp, fup, mup = ops.warp_mask(cu(d["c2"]), cu(d["flow_c"]), cu(d["mask_c"]), cu(d["deform_w"]), cu(d["deform_b"]),
+                                   cu(d["tradeoff"]), 20.0, 4.0, 2, 0.1, 0)
+    scale_w = max(1.0, float(np.abs(d["warp"]).max()))
+    assert np.abs(warp.cpu().numpy() - d["warp"]).max() <= 1e-4 * scale_w
+    for algo in (ops.CORR_SIMT, ops.CORR_MMA_BF16X3):
+        corr = ops.correlation(cu(d["c1"]), cu(d["warp"]), leaky_slope=0.1, algo=algo).cpu().numpy()
+        scale_c = max(1.0, float(np.abs(d["corr"]).max()))
+        assert np.abs(corr - d["corr"]).max() <= 1e-4 * scale_c, (algo, np.abs(corr - d["corr"]).max())
