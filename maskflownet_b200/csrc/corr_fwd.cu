@@ -435,14 +435,19 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1)
 //     continues a strip loads only its 8 new rows),
 //   * two stages of 8 data1 rows (pre-scaled by 1/C).
 // Software pipeline per tile, identical in every warp:
-//   1. issue the 16-byte global loads of the NEXT tile's rows into registers (5 octet-rows per warp: 80 KB in flight per SM)
+//   1. fire-and-forget `prefetch.global.L2` of the NEXT tile's 128-byte lines (no registers, no scoreboard: the DRAM reads
+//      run under the tensor work; a register prefetch here was measured NOT to overlap with the MMAs)
 //   2. current tile: B fragments (data1) by ldmatrix; walk the halo rows: each ldmatrix'ed A row (16 data2 positions x
 //      16 channels, hi and lo) feeds the MMAs of both pixel rows of the warp's item (2 rows x 8 pixels): hi*lo + lo*hi +
-//      hi*hi into fp32 accumulators; dy in passes of 3; per pass the accumulators go through a small staging buffer
-//      (predicated STS with lane-constant predicates, 16-byte LDS, LeakyReLU, 16-byte coalesced STG)
-//   3. split / transpose the prefetched registers into the ring and the other data1 stage
+//      hi*hi into fp32 accumulators; dy in passes of 3.  Per pass the four warps of a row pair drop their band pieces
+//      (predicated STS, lane-constant predicates) into a shared [plane][32 px] staging buffer and then store full
+//      128-byte plane rows (16-byte LDS, LeakyReLU, 16-byte STG: 4 lines per store instruction).
+//      Before the last pass the next tile's rows are pulled from L2 into registers: lane = pixel, 8 channels per load
+//      unit, every LDG covers whole sectors of 1-4 lines (2 data1 units + 2 data2 units + 1 halo-column unit per warp).
+//   3. split / transpose those registers into the ring and the other data1 stage (one STS.128 per 8 channels)
 //   4. __syncthreads
-// so global-load latency hides behind a whole tile of tensor work and no warp ever spins on a barrier.
+// Work assignment: each (n, x-strip) column of tiles is cut into equal pieces, one CTA per piece (level 2 of BASELINE
+// configs[1]: 64 strips x 2 pieces of 7 tiles = 128 CTAs), so only the first tile of a CTA loads its full halo.
 // =====================================================================================================
 namespace r4 {
 using tc::ldsm_x4;
@@ -711,6 +716,19 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
     }
   };
 
+  // fire-and-forget L2 prefetch of a continuing tile's lines (one 128-byte line per (row, channel)): threads 0..255 take
+  // the data1 rows, 256..511 the new data2 rows.  No register, no scoreboard: DRAM reads overlap the tensor work, and the
+  // register loads at the end of the current tile hit L2.
+  auto l2_prefetch_tile = [&](const TileGeo& t) {
+    const int tt = threadIdx.x & 255, row = tt >> 5, ch = tt & 31;
+    const bool second = threadIdx.x >= 256;
+    const int y = second ? t.y0 + MD + row : t.y0 + row;
+    if (ch < C && y < H) {
+      const float* p = (second ? d2 : d1) + ((size_t)t.n * C + ch) * plane + (size_t)y * W + t.x0;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  };
+
   // ---- prologue: bring in tile 0 completely ----
   int wr = 0;
   TileGeo cur = geo(0, wr);
@@ -733,7 +751,18 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
     float pe1[16], pe2[16], peh[8];
     if (has_next) {
       nxt = geo(s + 1, wr);   // always a continuing tile: its 8 new rows go to the 8 ring slots the current tile does not use
-      if (!(dbg & 2)) prefetch_next(nxt, pe1, pe2, peh);
+      if (!(dbg & 2)) {
+        if (dbg & 64) {   // profiling aid: conversion / stores without the global loads
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { pe1[c] = (float)c; pe2[c] = (float)(c + lane); }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) peh[c] = 1.f;
+        } else if (dbg & 256) {
+          prefetch_next(nxt, pe1, pe2, peh);   // previous scheme: register prefetch at tile start
+        } else {
+          l2_prefetch_tile(nxt);
+        }
+      }
     }
 
     // ---- 2. current tile ----
@@ -747,9 +776,12 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
     float* obase = out + (size_t)cur.n * out_bs + (size_t)yA * W + cur.x0;
     const bool two_k = C > 16;
 
-#pragma unroll 1
+#pragma unroll
     for (int ps = 0; ps < NPASS; ++ps) {
       const int d0 = ps * PASS;
+      // the next tile's lines were L2-prefetched at tile start: pull them into registers one pass before they are needed
+      // (short L2-hit latency, hidden behind the last pass)
+      if (ps == NPASS - 1 && has_next && !(dbg & (2 | 64 | 256 | 512))) prefetch_next(nxt, pe1, pe2, peh);
       float acc[2][PASS][4];
 #pragma unroll
       for (int rw = 0; rw < 2; ++rw)
@@ -846,7 +878,19 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
     }
 
     // ---- 3. split / transpose the prefetched rows (a fresh strip is fetched here, after everybody left the ring) ----
-    if (has_next && !(dbg & 2)) store_next(nxt, (s + 1) & 1, pe1, pe2, peh);
+    if (has_next && !(dbg & 2)) {
+      if (dbg & 128) {   // profiling aid: global loads without conversion / stores (keep the loads alive)
+        float acc0 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc0 += pe1[c] + pe2[c];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc0 += peh[c];
+        if (acc0 == 123.456f) out[0] = acc0;
+      } else {
+        if (dbg & 512) prefetch_next(nxt, pe1, pe2, peh);   // variant: L2-hit loads only at the very end of the tile
+        store_next(nxt, (s + 1) & 1, pe1, pe2, peh);
+      }
+    }
     cur = nxt;
     __syncthreads();
   }

@@ -15,7 +15,6 @@
 namespace mfn {
 
 namespace k3 {
-constexpr int NT = 256;        // threads (= pixels) per CTA
 constexpr int CC = 8;          // input channels per weight chunk
 constexpr int KC = CC * 9;     // k values per chunk
 }  // namespace k3
@@ -63,8 +62,9 @@ __device__ __forceinline__ Axis make_axis(float c, int n) {
 
 // SHARED: all nine taps use the same (dy, dx) (fused warp); otherwise per-tap offsets from `offset` (N,18,H,W).
 // FUSED epilogue operands (mask / tradeoff / conv_out / flow outputs) are only used when SHARED.
-template <int FT, int BORDER, bool SHARED>
-__global__ void __launch_bounds__(k3::NT, 2)
+// NT = threads (= pixels) per CTA: 256 for the big levels, 128 / 64 for the small ones so that the grid still covers the GPU
+template <int NT, int FT, int BORDER, bool SHARED>
+__global__ void __launch_bounds__(NT, 512 / NT)
     deform_fwd_kernel(const float* __restrict__ x, const float* __restrict__ offset,
                       const float* __restrict__ flow_c, const float* __restrict__ mask_c,
                       const float* __restrict__ weight, const float* __restrict__ bias,
@@ -338,24 +338,36 @@ static inline unsigned grid_for(long long total, int threads) {
   return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+template <int NT, int FT, int BORDER, bool SHARED>
+static void launch_deform_cfg(const float* x, const float* offset, const float* flow_c, const float* mask_c,
+                              const float* weight, const float* bias, const float* tradeoff, float* out, float* fup,
+                              float* mup, float* conv_out, int N, int C, int H, int W, int F, int up, float fs, float ls,
+                              float slope, cudaStream_t st) {
+  const long long total = (long long)N * H * W;
+  dim3 grid((unsigned)((total + NT - 1) / NT), (unsigned)((F + FT - 1) / FT));
+  deform_fwd_kernel<NT, FT, BORDER, SHARED><<<grid, NT, 0, st>>>(x, offset, flow_c, mask_c, weight, bias, tradeoff, out,
+                                                                fup, mup, conv_out, N, C, H, W, F, up, fs, ls, slope);
+}
+
 template <int BORDER, bool SHARED>
 static int launch_deform(const float* x, const float* offset, const float* flow_c, const float* mask_c,
                          const float* weight, const float* bias, const float* tradeoff, float* out, float* fup,
                          float* mup, float* conv_out, int N, int C, int H, int W, int F, int up, float fs, float ls,
                          float slope, cudaStream_t st) {
+  // pick (pixels per CTA, output channels per CTA) so that the grid has at least ~3 CTAs per SM; the coarse pyramid
+  // levels have only a few thousand pixels
   const long long total = (long long)N * H * W;
-  const unsigned gx = (unsigned)((total + k3::NT - 1) / k3::NT);
-  if (F <= 32) {
-    dim3 grid(gx, 1);
-    deform_fwd_kernel<32, BORDER, SHARED><<<grid, k3::NT, 0, st>>>(x, offset, flow_c, mask_c, weight, bias, tradeoff,
-                                                                  out, fup, mup, conv_out, N, C, H, W, F, up, fs, ls,
-                                                                  slope);
-  } else {
-    dim3 grid(gx, (F + 63) / 64);
-    deform_fwd_kernel<64, BORDER, SHARED><<<grid, k3::NT, 0, st>>>(x, offset, flow_c, mask_c, weight, bias, tradeoff,
-                                                                  out, fup, mup, conv_out, N, C, H, W, F, up, fs, ls,
-                                                                  slope);
-  }
+  const long long want = 3LL * kNumSMs;
+  auto ctas = [&](int nt, int ft) { return ((total + nt - 1) / nt) * ((F + ft - 1) / ft); };
+#define MFN_DEFORM_GO(NT_, FT_)                                                                                         \
+  launch_deform_cfg<NT_, FT_, BORDER, SHARED>(x, offset, flow_c, mask_c, weight, bias, tradeoff, out, fup, mup, conv_out, \
+                                              N, C, H, W, F, up, fs, ls, slope, st)
+  if (F > 32 && ctas(256, 64) >= want) MFN_DEFORM_GO(256, 64);
+  else if (ctas(256, 32) >= want) MFN_DEFORM_GO(256, 32);
+  else if (F > 32 && ctas(128, 64) >= want) MFN_DEFORM_GO(128, 64);
+  else if (ctas(128, 32) >= want) MFN_DEFORM_GO(128, 32);
+  else MFN_DEFORM_GO(64, 32);
+#undef MFN_DEFORM_GO
   return check_launch(SHARED ? "deform_fwd_kernel<shared-flow>" : "deform_fwd_kernel<per-tap>");
 }
 
