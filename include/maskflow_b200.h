@@ -185,6 +185,25 @@ MFN_API int mfn_image_warp_concat_forward(const float* im1, const float* im2, co
                                   const float* mask_q, float* c30, float* c40, int N, int Ci, int H,
                                   int W, float flow_scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Decoder dense-block convolution.
+ * replaces: the `conv` blocks of the decoder / context network, nn.Conv2D(3x3, stride 1, pad 1) + LeakyReLU(0.1)
+ *           (network/MaskFlownet.py:166-175) together with the concat that follows each of them,
+ *           x = F.concat(convL_i(x), x)  (:219-223, 237-241, 255-259, 273-277, 291-295).
+ * The input channels are read IN PLACE from a wider NCHW buffer (x_batch_stride = elements between samples) and the
+ * bias + LeakyReLU'ed output channels are written into another slice of (possibly the same) buffer, so the dense block
+ * needs no concat copies.  fp32-accurate tensor-core arithmetic (bf16 hi/lo split, 3 MMAs per product, fp32 accumulate).
+ * Weights are packed once per layer: mfn_conv3x3_packed_bytes() -> caller allocates -> mfn_conv3x3_pack_weights().
+ * Cout <= 128.  leaky_slope = 1 disables the activation.
+ * ------------------------------------------------------------------------------------------------- */
+MFN_API long long mfn_conv3x3_packed_bytes(int Cin, int Cout);
+MFN_API int mfn_conv3x3_pack_weights(const float* weight /* (Cout,Cin,3,3) */, void* packed, int Cin, int Cout,
+                                     void* stream);
+MFN_API int mfn_conv3x3_forward(const float* x, long long x_batch_stride, const void* packed_weight, const float* bias,
+                                float* out, long long out_batch_stride, int N, int Cin, int H, int W, int Cout,
+                                int dilation /* = padding; 1 for the decoder, 2..16 in the context network */,
+                                float leaky_slope, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

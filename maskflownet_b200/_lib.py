@@ -32,6 +32,8 @@ SIGNATURES = {
     "mfn_bilinear_sampler_forward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "mfn_image_warp_concat_forward": [_f] * 6 + [_i] * 4 + [_fl, _f],
     "mfn_set_tuning": [ctypes.c_char_p, _i],
+    "mfn_conv3x3_pack_weights": [_f, _f, _i, _i, _f],
+    "mfn_conv3x3_forward": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _fl, _f],
 }
 
 
@@ -60,6 +62,8 @@ def lib() -> ctypes.CDLL:
         L.mfn_last_error.restype = ctypes.c_char_p
         L.mfn_last_kernel.restype = ctypes.c_char_p
         L.mfn_launch_count.restype = ctypes.c_ulonglong
+        L.mfn_conv3x3_packed_bytes.restype = ctypes.c_longlong
+        L.mfn_conv3x3_packed_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
         for name, argtypes in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = argtypes

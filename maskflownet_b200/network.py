@@ -66,6 +66,21 @@ class DeformParams(nn.Module):
 
 
 class _FlowNetBase(nn.Module):
+    use_tc_conv = True   # inference: decoder / context 3x3 convolutions on the fp32-accurate tensor-core kernel (row N2)
+
+    def _packed(self, name):
+        """Packed split-bf16 weight image of conv `name`, rebuilt when the parameter changes."""
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        w = getattr(self, name).weight
+        key = (w.data_ptr(), w._version)
+        hit = cache.get(name)
+        if hit is None or hit[0] != key:
+            cache[name] = (key, ops.conv3x3_pack(w))
+        return cache[name][1]
+
+    def _fast(self, x):
+        return self.use_tc_conv and x.is_cuda and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
+
     def _pyramid(self, x, names):
         feats = []
         for lvl in range(1, 7):
@@ -75,13 +90,35 @@ class _FlowNetBase(nn.Module):
         return feats  # [c?1 .. c?6]
 
     def _dense(self, lvl, x):
+        """x = concat(leaky(conv_i(x)), x) five times (network/MaskFlownet.py:219-223 ...).  Inference: one pre-allocated
+        buffer, every convolution reads its input channels in place and writes its output in front of them."""
+        if self._fast(x):
+            N, Cb, H, W = x.shape
+            tot = sum(DECODER_CH)
+            buf = torch.empty((N, tot + Cb, H, W), device=x.device, dtype=torch.float32)
+            buf[:, tot:].copy_(x)
+            return self._dense_inplace(lvl, buf, tot)
         for i in range(5):
             x = torch.cat([tF.leaky_relu(getattr(self, f"conv{lvl}_{i}")(x), SLOPE), x], dim=1)
         return x
 
+    def _dense_inplace(self, lvl, buf, off):
+        """buf[:, off:] holds the block's input; returns buf filled front to back."""
+        Ctot = buf.shape[1]
+        for i, oc in enumerate(DECODER_CH):
+            conv = getattr(self, f"conv{lvl}_{i}")
+            ops.conv3x3_slices(buf, off, Ctot - off, self._packed(f"conv{lvl}_{i}"), conv.bias, buf, off - oc, oc, SLOPE)
+            off -= oc
+        return buf
+
     def _context(self, x):
+        fast = self._fast(x)
         for i in range(1, 7):
-            x = tF.leaky_relu(getattr(self, f"dc_conv{i}")(x), SLOPE)
+            conv = getattr(self, f"dc_conv{i}")
+            if fast:
+                x = ops.conv3x3(x, self._packed(f"dc_conv{i}"), conv.bias, conv.out_channels, SLOPE, conv.dilation[0])
+            else:
+                x = tF.leaky_relu(conv(x), SLOPE)
         return self.dc_conv7(x)
 
     def _make_decoder(self, in_ch: Dict[int, int], with_mask: bool, upfeat_ch):
@@ -139,27 +176,31 @@ class MaskFlownetS(_FlowNetBase):
         D = (2 * self.md + 1) ** 2
         if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
             corr = ops.correlation(f1, f2, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE)
-            return torch.cat([corr] + extras, dim=1) if extras else corr
+            return self._dense(lvl, torch.cat([corr] + extras, dim=1) if extras else corr)
         tot = D + sum(e.shape[1] for e in extras)
-        buf = torch.empty((N, tot, H, W), device=f1.device, dtype=torch.float32)
+        front = sum(DECODER_CH) if self.use_tc_conv else 0   # room for the dense block's outputs (written in place)
+        buf = torch.empty((N, front + tot, H, W), device=f1.device, dtype=torch.float32)
         hook = self.event_hook
         if hook is not None:
             hook("corr", lvl, 0)
-        ops.correlation(f1, f2, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE, out=buf[:, :D])
+        ops.correlation(f1, f2, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE,
+                        out=buf[:, front:front + D])
         if hook is not None:
             hook("corr", lvl, 1)
-        c = D
+        c = front + D
         for e in extras:
             buf[:, c:c + e.shape[1]].copy_(e)
             c += e.shape[1]
-        return buf
+        if front:
+            return self._dense_inplace(lvl, buf, front)
+        return self._dense(lvl, buf)
 
     def forward(self, im1: torch.Tensor, im2: torch.Tensor, want_cascade_inputs: bool = False):
         """Returns (predictions [flow6..flow2, each * scale], [sigmoid(mask2)], srcs or None) like the reference
         (network/MaskFlownet.py:302-315).  srcs (needed only by the cascade) is built when want_cascade_inputs."""
         c1 = self._pyramid(im1, "abc")
         c2 = self._pyramid(im2, "abc")
-        x = self._dense(6, self._corr_block(6, c1[5], c2[5], []))
+        x = self._corr_block(6, c1[5], c2[5], [])   # correlation + dense block
         flow = self.pred_flow6(x)
         mask = self.pred_mask6(x)
         flows = [flow]
@@ -173,7 +214,7 @@ class MaskFlownetS(_FlowNetBase):
                                              float(STRIDES[lvl]), 2, SLOPE, self.border_mode)
             if self.event_hook is not None:
                 self.event_hook("warp", lvl, 1)
-            x = self._dense(lvl, self._corr_block(lvl, c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up]))
+            x = self._corr_block(lvl, c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up])
             flow = flow_up + getattr(self, f"pred_flow{lvl}")(x)
             if lvl > 2:
                 mask = getattr(self, f"pred_mask{lvl}")(x)

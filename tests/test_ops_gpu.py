@@ -335,3 +335,70 @@ def test_real_checkpoint_distribution_level2():
         corr = ops.correlation(cu(d["c1"]), cu(d["warp"]), leaky_slope=0.1, algo=algo).cpu().numpy()
         scale_c = max(1.0, float(np.abs(d["corr"]).max()))
         assert np.abs(corr - d["corr"]).max() <= 1e-4 * scale_c, (algo, np.abs(corr - d["corr"]).max())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# decoder dense-block convolution (row N2)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(1, 81, 128, 7, 16), (2, 131, 128, 12, 40), (1, 35, 32, 9, 33),
+                                            (2, 64, 96, 8, 32), (1, 579, 128, 10, 24), (1, 16, 64, 5, 7)])
+def test_conv3x3_tensor_core_matches_fp32(N, Cin, Cout, H, W):
+    """fp32-accurate (bf16x3) tensor-core convolution vs a float64 convolution of the same operands."""
+    rng = np.random.default_rng(31)
+    x = feat(rng, (N, Cin, H, W))
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(),
+                                     torch.from_numpy(b).double(), padding=1)
+    ref = torch.nn.functional.leaky_relu(ref, 0.1).float().numpy()
+    packed = ops.conv3x3_pack(cu(w))
+    got = ops.conv3x3(cu(x), packed, cu(b), Cout, 0.1).cpu().numpy()
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(got - ref).max() <= 1e-4 * scale, np.abs(got - ref).max()
+    # for context: error of a TF32 convolution (what "allow_tf32" would do) is two orders of magnitude larger
+    torch.backends.cudnn.allow_tf32 = True
+    tf32 = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(cu(x), cu(w), cu(b), padding=1), 0.1).cpu().numpy()
+    torch.backends.cudnn.allow_tf32 = False
+    assert np.abs(got - ref).max() <= 0.25 * max(np.abs(tf32 - ref).max(), 1e-5 * scale)
+
+
+@pytest.mark.parametrize("dil", [2, 4, 8, 16])
+def test_conv3x3_dilated(dil):
+    """context-network convolutions (dc_conv2..5: dilation = padding = 2, 4, 8, 16; network/MaskFlownet.py:133-137)"""
+    rng = np.random.default_rng(33 + dil)
+    N, Cin, Cout, H, W = 2, 40, 96, 21, 45
+    x = feat(rng, (N, Cin, H, W))
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(),
+                                     torch.from_numpy(b).double(), padding=dil, dilation=dil)
+    ref = torch.nn.functional.leaky_relu(ref, 0.1).float().numpy()
+    got = ops.conv3x3(cu(x), ops.conv3x3_pack(cu(w)), cu(b), Cout, 0.1, dilation=dil).cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_conv3x3_in_place_concat_block():
+    """The dense block: five convolutions reading / writing channel slices of one buffer == torch.cat chain."""
+    rng = np.random.default_rng(32)
+    N, Cb, H, W = 2, 40, 9, 20
+    chans = (24, 16, 8)
+    x = feat(rng, (N, Cb, H, W))
+    ws = []
+    c = Cb
+    for oc in chans:
+        ws.append(((rng.standard_normal((oc, c, 3, 3)) * np.sqrt(2.0 / (9 * c))).astype(np.float32),
+                   (rng.standard_normal(oc) * 0.1).astype(np.float32)))
+        c += oc
+    ref = torch.from_numpy(x)
+    for w, b in ws:
+        y = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(ref, torch.from_numpy(w), torch.from_numpy(b), padding=1), 0.1)
+        ref = torch.cat([y, ref], dim=1)
+    tot = sum(chans)
+    buf = torch.full((N, tot + Cb, H, W), float("nan"), device=DEV)
+    buf[:, tot:] = cu(x)
+    off = tot
+    for (w, b), oc in zip(ws, chans):
+        ops.conv3x3_slices(buf, off, tot + Cb - off, ops.conv3x3_pack(cu(w)), cu(b), buf, off - oc, oc, 0.1)
+        off -= oc
+    assert off == 0
+    assert np.abs(buf.cpu().numpy() - ref.numpy()).max() <= 2e-4
