@@ -232,8 +232,10 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1)
     const uint32_t wst = wt_u32 + (uint32_t)((it % WSTAGES) * WT_BYTES);
     const uint32_t ist = PT ? in_u32 + (uint32_t)((it & 1) * IN_STAGE + wr * (HWP * PXB))
                             : in_u32 + (uint32_t)((q & 1) * IN_STAGE + (wr + ky) * (HWP * PXB));
+    const bool half_chunk = 32 * q + 16 >= Cin;   // the upper 16 channels of the last chunk are padding: skip their MMAs
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
+      if (kk == 1 && half_chunk) break;
       uint32_t ah[2][4], al[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
