@@ -265,7 +265,7 @@ def main():
                      "hot_path_share_of_step": round(hot_ms / (ms_total / K), 4),
                      "per_kernel_ms": {f"{k[0]}{k[1]}": round(v, 5) for k, v in sorted(kt.items())}},
     }
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.cpu_sample_steps > 0:
         try:
             val, sec, used = cpu_arm(args.cpu_sample_steps, 1, host_threads)
             line["cpu_baseline"] = {"value": round(val, 4), "unit": "pairs/s", "cores": used, "kind": "port",

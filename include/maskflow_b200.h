@@ -136,6 +136,15 @@ MFN_API int mfn_warp_mask_forward(const float* x, const float* flow_coarse, cons
                           int H, int W, int F, int upsample_factor, float flow_scale,
                           float level_stride, float leaky_slope, int border_mode, void* stream);
 
+/* Tensor-core variant of mfn_warp_mask_forward (same arguments and results; fp32-accurate bf16x3 arithmetic): `weight` is
+ * replaced by the packed image of the (F,C,3,3) deformable-convolution weight produced by mfn_conv3x3_pack_weights
+ * (mfn_conv3x3_packed_bytes(C, F) bytes).  F <= 128.  Inference path (no saved tensors needed beyond conv_out). */
+MFN_API int mfn_warp_mask_forward_tc(const float* x, const float* flow_coarse, const float* mask_coarse,
+                                     const void* packed_weight, const float* bias, const float* tradeoff, float* out,
+                                     float* flow_up_out, float* mask_up_out, float* conv_out, int N, int C, int H, int W,
+                                     int F, int upsample_factor, float flow_scale, float level_stride, float leaky_slope,
+                                     int border_mode, void* stream);
+
 /* Backward of mfn_warp_mask_forward.
  *   in : grad_out (N,F,H,W); out (forward result); conv_out (saved); x; flow_up (N,2,H,W, the forward's
  *        flow_up_out); mask_up (N,1,H,W) or NULL; weight

@@ -25,6 +25,7 @@ SIGNATURES = {
     "mfn_deformable_conv_forward": [_f, _f, _f, _f, _f] + [_i] * 16 + [_f],
     "mfn_deformable_conv_backward": [_f] * 8 + [_i] * 6 + [_f],
     "mfn_warp_mask_forward": [_f] * 10 + [_i] * 6 + [_fl, _fl, _fl, _i, _f],
+    "mfn_warp_mask_forward_tc": [_f] * 10 + [_i] * 6 + [_fl, _fl, _fl, _i, _f],
     "mfn_warp_mask_backward": [_f] * 14 + [_i] * 5 + [_fl, _fl, _fl, _i, _f],
     "mfn_upsample_forward": [_f, _f, _i, _i, _i, _i, _fl, _f],
     "mfn_upsample_backward": [_f, _f, _i, _i, _i, _i, _fl, _f],

@@ -211,7 +211,10 @@ class MaskFlownetS(_FlowNetBase):
             if self.event_hook is not None:
                 self.event_hook("warp", lvl, 0)
             warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, mask, dp.weight, dp.bias, trade, self.scale,
-                                             float(STRIDES[lvl]), 2, SLOPE, self.border_mode)
+                                             float(STRIDES[lvl]), 2, SLOPE, self.border_mode,
+                                             # tensor-core variant pays off from 64 channels on (measured: C=32 is gather-bound)
+                                             packed_weight=self._packed(f"deform{lvl}")
+                                             if (self._fast(flow) and dp.weight.shape[0] >= 64) else None)
             if self.event_hook is not None:
                 self.event_hook("warp", lvl, 1)
             x = self._corr_block(lvl, c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up])

@@ -402,3 +402,31 @@ def test_conv3x3_in_place_concat_block():
         off -= oc
     assert off == 0
     assert np.abs(buf.cpu().numpy() - ref.numpy()).max() <= 2e-4
+
+
+@pytest.mark.parametrize("N,C,F,H,W", [(2, 32, 32, 12, 16), (1, 64, 64, 8, 36), (1, 96, 96, 6, 8), (1, 128, 128, 9, 33),
+                                       (1, 20, 24, 7, 9)])
+@pytest.mark.parametrize("border", [0, 1])
+def test_warp_mask_tensor_core_forward(N, C, F, H, W, border):
+    """tensor-core fused warp (packed weights) vs the oracle; H, W even for the Upsample(2) of flow / mask"""
+    H, W = H + (H % 2), W + (W % 2)
+    rng = np.random.default_rng(41)
+    x, w, b, flow, mask, trade = _level_inputs(rng, N, C, F, H, W)
+    flow = flow * 4          # several pixels of displacement: many taps leave the image
+    t = torch.from_numpy
+    ref, rflow, rmask = torch_ref.warp_mask(t(x), t(flow), t(mask), t(w), t(b), t(trade), 20.0, 4, 2, border)
+    with torch.no_grad():
+        out, fup, mup = ops.warp_mask(cu(x), cu(flow), cu(mask), cu(w), cu(b), cu(trade), 20.0, 4.0, 2, 0.1, border,
+                                      packed_weight=ops.conv3x3_pack(cu(w)))
+    assert "warp_mma" in _lib.last_kernel()
+    assert np.abs(fup.cpu().numpy() - rflow.numpy()).max() <= 1e-6
+    assert np.abs(mup.cpu().numpy() - rmask.numpy()).max() <= 1e-6
+    scale = max(1.0, float(ref.abs().max()))
+    assert np.abs(out.cpu().numpy() - ref.numpy()).max() <= 1e-4 * scale
+    # cascade variant: no mask / trade-off, no upsampling
+    ref2, _, _ = torch_ref.warp_mask(t(x), t(rflow.numpy()), None, t(w), t(b), None, 20.0, 8, 1, border)
+    with torch.no_grad():
+        out2, _, m2 = ops.warp_mask(cu(x), cu(rflow.numpy()), None, cu(w), cu(b), None, 20.0, 8.0, 1, 0.1, border,
+                                    packed_weight=ops.conv3x3_pack(cu(w)))
+    assert m2 is None
+    assert np.abs(out2.cpu().numpy() - ref2.numpy()).max() <= 1e-4 * max(1.0, float(ref2.abs().max()))
