@@ -42,6 +42,18 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def dram_traffic(kernel_name: str):
+    """dram read+write bytes per launch of the dominant kernel, from the committed ncu capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    try:
+        for key, rec in json.load(open(p)).items():
+            if not key.startswith("_") and key in (kernel_name or ""):
+                return int(rec["dram_read_bytes"]) + int(rec["dram_write_bytes"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -193,12 +205,14 @@ def main():
         n0 = _lib.launch_count()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.profiler.start()   # cudaProfilerStart: lets `ncu --profile-from-start off` list exactly the timed launches
         e0.record()
         for _ in range(K):
             flush.zero_()             # L2 flush between steps (inside the timed region, ~0.05 ms per step)
             step_resident()
         e1.record()
         barrier()
+        torch.cuda.profiler.stop()
         ms_total = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
         launches = _lib.launch_count() - n0
         model.event_hook = None
@@ -257,7 +271,7 @@ def main():
         "clocks": sampler.summary(),
         "roofline": {"kernel": f"{corr_kernel} (level-2 correlation, N=8 C=32 112x256, md=4)", "bound": "hbm",
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4) if achieved else None, "traffic": None,
+                     "frac": round(achieved / peak, 4) if achieved else None, "traffic": dram_traffic(corr_kernel),
                      "peak_source": peak_kind, "alg_bytes_per_launch": alg_bytes,
                      "launch_ms_in_step": round(t_corr2, 5) if t_corr2 else None,
                      "launch_ms_isolated_cold_l2": round(sum(iso) / len(iso), 5),
