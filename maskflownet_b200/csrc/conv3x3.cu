@@ -279,11 +279,16 @@ static int launch_conv(const float* x, long long x_bs, const unsigned char* wpac
                   : launch_conv_impl<WC, NTN, true>(x, x_bs, wpack, bias, out, out_bs, N, Cin, H, W, Cout, dil, slope, st);
 }
 
+// bytes of the mma.sync weight image (first region of the packed buffer; the tcgen05 image follows it)
+long long conv3x3_sync_packed_bytes(int Cin, int Cout) {
+  return (long long)((Cin + 31) / 32) * 9 * 2 * c3::cout_pad(Cout) * c3::PXB;
+}
+
 }  // namespace mfn
 
 extern "C" long long mfn_conv3x3_packed_bytes(int Cin, int Cout) {
   if (Cin <= 0 || Cout <= 0) return 0;
-  return (long long)((Cin + 31) / 32) * 9 * 2 * mfn::c3::cout_pad(Cout) * mfn::c3::PXB;
+  return mfn::conv3x3_sync_packed_bytes(Cin, Cout) + mfn::conv3x3_umma_packed_bytes(Cin, Cout);
 }
 
 extern "C" int mfn_conv3x3_pack_weights(const float* weight, void* packed, int Cin, int Cout, void* stream) {
@@ -297,7 +302,10 @@ extern "C" int mfn_conv3x3_pack_weights(const float* weight, void* packed, int C
   if (blocks > 4096) blocks = 4096;
   conv3x3_pack_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(weight, static_cast<unsigned char*>(packed), Cin,
                                                                        Cout, CoutP, nChunks);
-  return check_launch("conv3x3_pack_kernel");
+  const int rc = check_launch("conv3x3_pack_kernel");
+  if (rc) return rc;
+  return conv3x3_umma_pack(weight, static_cast<unsigned char*>(packed) + conv3x3_sync_packed_bytes(Cin, Cout), Cin, Cout,
+                           as_stream(stream));
 }
 
 extern "C" int mfn_conv3x3_forward(const float* x, long long x_batch_stride, const void* packed_weight,
@@ -316,6 +324,11 @@ extern "C" int mfn_conv3x3_forward(const float* x, long long x_batch_stride, con
               "mfn_conv3x3_forward: batch stride smaller than the tensor");
   const unsigned char* wp = static_cast<const unsigned char*>(packed_weight);
   cudaStream_t st = as_stream(stream);
+  if (tuning().conv_umma && W >= tuning().conv_umma_min_w) {   // tcgen05 / TMEM kernel
+    const int rc = conv3x3_umma_launch(x, xbs, wp + conv3x3_sync_packed_bytes(Cin, Cout), bias, out, obs, N, Cin, H, W,
+                                       Cout, dilation, leaky_slope, st);
+    if (rc != -1) return rc;
+  }
   const int nt = (Cout + 7) / 8;   // n8 tiles needed
   if (nt <= 4) return launch_conv<1, 4>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, st);
   if (nt <= 8) return launch_conv<1, 8>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, st);

@@ -1,0 +1,338 @@
+// conv3x3_umma.cu -- the decoder / context-network 3x3 convolution on the 5th-generation
+// tensor cores: tcgen05.mma with the accumulators in tensor memory (TMEM).  Same contract as conv3x3.cu (channel slices of
+// a level buffer in, bias + LeakyReLU'ed channel slice out, fp32-accurate through the bf16 hi/lo split: three MMAs
+// hi*lo + lo*hi + hi*hi per product), reference call sites network/MaskFlownet.py:203-300.
+//
+// Implicit GEMM without im2col:   D[pixel, f] = sum_{tap, c} X[pixel + tap offset, c] * Wt[tap][c][f]
+//   * M tile = 128 consecutive pixels of one image row, a CTA owns R = 2 rows x 128 pixels x all (<= 128) output channels:
+//     two 128 x N fp32 accumulators in TMEM (2N <= 256 columns, so two CTAs share an SM: one CTA's epilogue and prologue
+//     run under the other's MMAs).
+//   * K is walked as (16-channel chunk) x (tap).  Per chunk the producers (6 warps) convert the input rows the nine taps
+//     touch -- (R + 2d) rows (or 3R for large dilations) x (128 + 2d) pixels -- from fp32 NCHW into split bf16 in the
+//     *no-swizzle K-major core-matrix layout*: plane [8-channel group][pixel] with 16 bytes per entry.  In that layout a
+//     tap shift is nothing but a different start address (+16 bytes per pixel), so all nine taps are nine shared-memory
+//     descriptors over ONE converted tile: (start, LBO = plane pitch, SBO = 128 B).
+//   * weights are pre-packed (mfn_conv3x3_pack_weights) into per-(chunk, tap) images of the same layout and streamed by
+//     one thread with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) through a 4-stage ring.
+//   * one thread issues the MMAs (M=128, N=CoutP, K=16, kind::f16, bf16 x bf16 -> fp32); tcgen05.commit releases the
+//     weight / input stages and finally signals the epilogue warps, which read the accumulators with tcgen05.ld
+//     (lane = pixel, 32 output channels per instruction), add the bias, apply LeakyReLU and store NCHW (coalesced 128 B
+//     per plane row and warp).
+#include "mma_tiles.cuh"
+
+namespace mfn {
+namespace um {
+using c3::smem_u32;
+using c3::split_pair;
+
+constexpr int MT = 128;          // pixels per M tile
+constexpr int R = 2;             // output rows per CTA
+constexpr int NTHREADS = 256;
+constexpr int NPROD = 6;         // producer warps (warps 2..7); warps 4..7 double as epilogue warps
+constexpr int WSTAGES = 4;
+constexpr int BATCH = 4;         // producer items (32 entries x 8 channels) in flight per warp
+
+__host__ __device__ inline int n_slots(int dil) { return dil >= R ? 3 * R : R + 2 * dil; }
+__host__ __device__ inline int slot_of(int r, int ky, int dil) { return dil >= R ? ky * R + r : r + ky * dil; }
+__host__ __device__ inline int row_of_slot(int slot, int y0, int dil) {
+  return dil >= R ? y0 + (slot % R) + (slot / R - 1) * dil : y0 - dil + slot;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// shared-memory matrix descriptor, no swizzle, K-major: 8-row x 16-byte core matrices; SBO = distance between 8-row
+// groups (M/N direction), LBO = distance between the two 8-element K groups of one MMA (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct SmemMap {
+  int a_lo, a_stage, w_tile, w_off, bar_off, total;
+};
+__host__ __device__ inline SmemMap smem_map(int E, int CoutP) {
+  SmemMap m;
+  m.a_lo = 2 * E * 16;              // hi image: two 8-channel planes of E entries
+  m.a_stage = 2 * m.a_lo;           // hi + lo
+  m.w_tile = 64 * CoutP;            // [hi | lo][2 planes][CoutP][16 B]
+  m.w_off = 2 * m.a_stage;
+  m.bar_off = m.w_off + WSTAGES * m.w_tile;
+  m.total = m.bar_off + 16 * 8;
+  return m;
+}
+}  // namespace um
+
+// UMMA weight image: [16-channel chunk c][tap][hi | lo][8-channel plane kc][f (CoutP)][8 x bf16 = 16 bytes]
+__global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned char* __restrict__ packed, int Cin, int Cout,
+                                         int CoutP, int nChunks16) {
+  const long long total = (long long)nChunks16 * 9 * CoutP * 8;   // (c, tap, f, channel pair)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);                     // channel pair inside the chunk
+    const int f = (int)((i >> 3) % CoutP);
+    const int tap = (int)((i / (8LL * CoutP)) % 9);
+    const int c = (int)(i / (8LL * CoutP * 9));
+    const int ch = 16 * c + 2 * j;
+    float a = 0.f, b = 0.f;
+    if (f < Cout) {
+      if (ch < Cin) a = w[((size_t)f * Cin + ch) * 9 + tap];
+      if (ch + 1 < Cin) b = w[((size_t)f * Cin + ch + 1) * 9 + tap];
+    }
+    uint32_t hi, lo;
+    c3::split_pair(a, b, hi, lo);
+    const int wt = 64 * CoutP;
+    unsigned char* tile = packed + ((size_t)c * 9 + tap) * wt;
+    const int off = (j >> 2) * (CoutP * 16) + f * 16 + (j & 3) * 4;
+    *reinterpret_cast<uint32_t*>(tile + off) = hi;
+    *reinterpret_cast<uint32_t*>(tile + wt / 2 + off) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(um::NTHREADS, 2)
+    conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
+                        const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
+                        int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int dil, int tmem_cols) {
+  using namespace um;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nslots = n_slots(dil), PW = MT + 2 * dil, E = nslots * PW;
+  const SmemMap sm = smem_map(E, CoutP);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar0 = s_base + sm.bar_off;
+  // barriers: a_full[2] @0,8  a_empty[2] @16,24  w_full[4] @32..  w_empty[4] @64..  acc_full @96;  tmem pointer @104
+  const uint32_t a_full = bar0, a_empty = bar0 + 16, w_full = bar0 + 32, w_empty = bar0 + 64, acc_full = bar0 + 96;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + sm.bar_off + 104);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+  const int x0 = tx * MT, y0 = ty * R;
+  const size_t plane = (size_t)H * W;
+  const int nIter = nChunks * 9;
+
+  if (tid == 0) {
+    mbar_init(a_full, NPROD);
+    mbar_init(a_full + 8, NPROD);
+    mbar_init(a_empty, 1);
+    mbar_init(a_empty + 8, 1);
+    for (int i = 0; i < WSTAGES; ++i) {
+      mbar_init(w_full + 8 * i, 1);
+      mbar_init(w_empty + 8 * i, 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {   // TMEM allocation: one warp, address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + sm.bar_off + 104),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ MMA issuer (one thread) ============================
+    if (lane == 0) {
+      // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), K-major both, N >> 3 @17, M >> 4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CoutP >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+      const uint32_t a_lbo = (uint32_t)E * 16u, b_lbo = (uint32_t)CoutP * 16u;
+      for (int c = 0; c < nChunks; ++c) {
+        mbar_wait(a_full + 8 * (c & 1), (uint32_t)((c >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_st = s_base + (uint32_t)((c & 1) * sm.a_stage);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int it = c * 9 + tap, ws = it % WSTAGES;
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          mbar_wait(w_full + 8 * ws, (uint32_t)((it / WSTAGES) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t w_st = s_base + (uint32_t)(sm.w_off + ws * sm.w_tile);
+          const uint64_t b_hi = smem_desc(w_st, b_lbo, 128), b_lo = smem_desc(w_st + (uint32_t)(sm.w_tile / 2), b_lbo, 128);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const uint32_t a_addr = a_st + (uint32_t)((slot_of(r, ky, dil) * PW + kx * dil) * 16);
+            const uint64_t a_hi = smem_desc(a_addr, a_lbo, 128), a_lo = smem_desc(a_addr + (uint32_t)sm.a_lo, a_lbo, 128);
+            const uint32_t d = tmem_base + (uint32_t)(r * CoutP);
+            umma_bf16(d, a_hi, b_lo, idesc, it > 0 ? 1u : 0u);
+            umma_bf16(d, a_lo, b_hi, idesc, 1u);
+            umma_bf16(d, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(w_empty + 8 * ws);       // weight stage free once these MMAs have read it
+        }
+        umma_commit(a_empty + 8 * (c & 1));    // input stage free
+      }
+      umma_commit(acc_full);                   // accumulators complete
+    }
+  } else if (warp == 1) {
+    // ============================ weight loader (one thread) ============================
+    if (lane == 0) {
+      for (int it = 0; it < nIter; ++it) {
+        const int ws = it % WSTAGES;
+        if (it >= WSTAGES) mbar_wait(w_empty + 8 * ws, (uint32_t)(((it / WSTAGES) + 1) & 1));
+        mbar_arrive_expect_tx(w_full + 8 * ws, (uint32_t)sm.w_tile);
+        bulk_g2s(s_base + (uint32_t)(sm.w_off + ws * sm.w_tile), wpack + (size_t)it * sm.w_tile, (uint32_t)sm.w_tile,
+                 w_full + 8 * ws);
+      }
+    }
+  } else {
+    // ============================ input producers (warps 2..7) ============================
+    const int pw = warp - 2;
+    const float* xn = x + (size_t)n * x_bs;
+    const int G = (E + 31) / 32, nItems = 2 * G;       // item = (32 entries, 8-channel plane)
+    for (int c = 0; c < nChunks; ++c) {
+      if (c >= 2) mbar_wait(a_empty + 8 * (c & 1), (uint32_t)(((c >> 1) + 1) & 1));
+      unsigned char* a_st = smem + (c & 1) * sm.a_stage;
+      for (int k0 = pw; k0 < nItems; k0 += NPROD * BATCH) {
+        float v[BATCH][8];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int t = k0 + b * NPROD;
+          const int kc = t & 1, e = (t >> 1) * 32 + lane;
+          const int slot = e / PW, p = e - slot * PW;
+          const int y = row_of_slot(slot, y0, dil), xx = x0 - dil + p;
+          const bool ok = t < nItems && e < E && y >= 0 && y < H && xx >= 0 && xx < W;
+          const int c0 = 16 * c + 8 * kc;
+          const float* src = xn + (size_t)c0 * plane + (size_t)(ok ? y : 0) * W + (ok ? xx : 0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[b][j] = (ok && c0 + j < Cin) ? __ldg(src) : 0.f;
+            src += plane;
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int t = k0 + b * NPROD;
+          const int kc = t & 1, e = (t >> 1) * 32 + lane;
+          if (t < nItems && e < E) {
+            uint4 hi, lo;
+            split_pair(v[b][0], v[b][1], hi.x, lo.x);
+            split_pair(v[b][2], v[b][3], hi.y, lo.y);
+            split_pair(v[b][4], v[b][5], hi.z, lo.z);
+            split_pair(v[b][6], v[b][7], hi.w, lo.w);
+            unsigned char* dst = a_st + (kc * E + e) * 16;
+            *reinterpret_cast<uint4*>(dst) = hi;
+            *reinterpret_cast<uint4*>(dst + sm.a_lo) = lo;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + 8 * (c & 1));
+    }
+    // ============================ epilogue (warps 4..7: TMEM lanes 32*(warp&3) ..) ============================
+    if (warp >= 4) {
+      mbar_wait(acc_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int q = warp & 3;
+      const int xx = x0 + 32 * q + lane;
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        const int y = y0 + r;
+        float* on = out + (size_t)n * out_bs + (size_t)y * W + xx;
+        const bool okp = y < H && xx < W;
+#pragma unroll 1
+        for (int nc = 0; nc < CoutP / 32; ++nc) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(r * CoutP + nc * 32), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int f = nc * 32 + j;
+            if (f < Cout && okp) {
+              const float b = bias ? __ldg(bias + f) : 0.f;
+              on[(size_t)f * plane] = leaky(__uint_as_float(v[j]) + b, slope);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+long long conv3x3_umma_packed_bytes(int Cin, int Cout) {
+  return (long long)((Cin + 15) / 16) * 9 * 64 * c3::cout_pad(Cout);
+}
+
+int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int Cout, cudaStream_t st) {
+  const int CoutP = c3::cout_pad(Cout), nChunks16 = (Cin + 15) / 16;
+  const long long total = (long long)nChunks16 * 9 * CoutP * 8;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  conv3x3_pack_umma_kernel<<<(unsigned)blocks, 256, 0, st>>>(weight, packed, Cin, Cout, CoutP, nChunks16);
+  return check_launch("conv3x3_pack_umma_kernel");
+}
+
+// returns -1 when the shape does not fit this kernel (caller falls back to the mma.sync kernel)
+int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
+                        long long out_bs, int N, int Cin, int H, int W, int Cout, int dil, float slope, cudaStream_t st) {
+  using namespace um;
+  const int CoutP = c3::cout_pad(Cout), nChunks = (Cin + 15) / 16;
+  const int E = n_slots(dil) * (MT + 2 * dil);
+  const SmemMap sm = smem_map(E, CoutP);
+  if (sm.total > 227 * 1024 || E * 16 > 0x3FFF * 16) return -1;
+  static int configured = 0;
+  if (configured < sm.total) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(conv3x3_umma_kernel): %s", cudaGetErrorString(e));
+    configured = sm.total;
+  }
+  int cols = 32;
+  while (cols < R * CoutP) cols *= 2;
+  const int tilesX = (W + MT - 1) / MT, tilesY = (H + R - 1) / R;
+  const unsigned grid = (unsigned)((long long)N * tilesX * tilesY);
+  conv3x3_umma_kernel<<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, Cout, CoutP, nChunks,
+                                                        slope, tilesX, tilesY, dil, cols);
+  return check_launch("conv3x3_umma_kernel");
+}
+
+}  // namespace mfn

@@ -454,32 +454,41 @@ using tc::ldsm_x4;
 using tc::mma_bf16;
 using tc::smem_u32;
 using tc::split_pair;
-constexpr int TH = 8, TW = 32, HX = 4, HWP = TW + 2 * HX;
-constexpr int NWARPS = 16, NTHREADS = 32 * NWARPS;
+using tc::mbar_init;
+using tc::mbar_arrive;
+using tc::mbar_wait;
+// Two shapes, selected by the tile height TH (template parameter of the kernel):
+//   TH = 8: 16 warps, 1 CTA per SM, 24-row ring, two data1 stages (the original shape)
+//   TH = 4:  8 warps, 2 CTAs per SM (<= 113 KB shared memory and 128 registers each), 16-row ring, one data1 stage
+//            guarded by an mbarrier -- two independent CTAs per SM drift apart, so one CTA's loads / epilogue run under
+//            the other's tensor work.
+constexpr int TW = 32, HX = 4, HWP = TW + 2 * HX;
 constexpr int PXB = 64;                          // bytes per pixel (32 channels bf16), no padding
-constexpr int R = 24;                            // ring rows
 constexpr int ROW_BYTES = HWP * PXB;             // 2560: one split row (hi or lo)
-constexpr int RING_LO = R * ROW_BYTES;
-constexpr int RING_BYTES = 2 * RING_LO;
 constexpr int F1_ROW_BYTES = TW * PXB;           // 2048
-constexpr int F1_LO = TH * F1_ROW_BYTES;
-constexpr int F1_STAGE = 2 * F1_LO;              // hi + lo of one stage
 constexpr int PASS = 3;
 constexpr int SSTR = TW + 4;                     // staging row: the tile's 32 pixels + 4 pad (keeps float4 alignment)
-constexpr int UNITS_F1 = TH * 4;                 // load units (32 lanes x 8 channels) of the data1 rows
-constexpr int UPW = 5;                           // units per warp per batch: 32 + 6*8 = 80 = 16 warps x 5
-static_assert(UNITS_F1 + 6 * TH == UPW * NWARPS, "unit split of a continuing tile must be exact");
+constexpr int UPW = 5;                           // units per warp per batch: 4*TH + 6*TH = 10*TH = 2*TH warps x 5
+__host__ __device__ constexpr int ring_rows(int th) { return 2 * th + 8; }       // halo rows of a tile (md = 4) + TH new rows
+__host__ __device__ constexpr int f1_stages(int th) { return th == 8 ? 2 : 1; }
 __host__ __device__ constexpr int stg_group_bytes(int md) { return 2 * PASS * (2 * md + 1) * SSTR * 4; }  // 2 buffers
-__host__ __device__ constexpr int smem_bytes(int md) { return RING_BYTES + 2 * F1_STAGE + 4 * stg_group_bytes(md); }
+__host__ __device__ constexpr int smem_bytes(int md, int th) {
+  return 2 * ring_rows(th) * ROW_BYTES + f1_stages(th) * 2 * th * F1_ROW_BYTES + (th / 2) * stg_group_bytes(md) + 16;
+}
 __device__ __forceinline__ int swz(int p, int c) { return p * PXB + ((c ^ ((p >> 1) & 3)) << 4); }
 }  // namespace r4
 
-template <int MD, bool VEC>
-__global__ void __launch_bounds__(r4::NTHREADS, 1)
+template <int MD, bool VEC, int TH>
+__global__ void __launch_bounds__(64 * TH, TH == 8 ? 1 : 2)
     corr_mma_ring_kernel(const float* __restrict__ d1, const float* __restrict__ d2, float* __restrict__ out,
                          int N, int C, int H, int W, long long out_bs, float slope, int tilesX, int tilesY,
                          int numTiles, int ovec, int dbg) {
   using namespace r4;
+  constexpr int NWARPS = 2 * TH, NTHREADS = 32 * NWARPS;
+  constexpr int R = ring_rows(TH), RING_LO = R * ROW_BYTES, RING_BYTES = 2 * RING_LO;
+  constexpr int F1_LO = TH * F1_ROW_BYTES, F1_STAGE = 2 * F1_LO, F1_STAGES = f1_stages(TH);
+  constexpr int UNITS_F1 = TH * 4;                 // load units (32 lanes x 8 channels) of the data1 rows
+  static_assert(UNITS_F1 + 6 * TH == UPW * NWARPS, "unit split of a continuing tile must be exact");
   constexpr int G = 2 * MD + 1;
   constexpr int HR = TH + 2 * MD;
   constexpr int NPASS = (G + PASS - 1) / PASS;
@@ -618,7 +627,13 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
     sto[i] = dxi * SSTR + 8 * oc + 2 * j + (i & 1);
   }
   // the four warps of a row pair share a staging area (two buffers: one per pixel row) and a named barrier
-  float* stg_g = reinterpret_cast<float*>(smem_raw + RING_BYTES + 2 * F1_STAGE) + rp * (2 * SROWS * SSTR);
+  float* stg_g = reinterpret_cast<float*>(smem_raw + RING_BYTES + F1_STAGES * F1_STAGE) + rp * (2 * SROWS * SSTR);
+  // single data1 stage: the next tile's data1 rows may only be written once every warp holds its B fragments
+  const uint32_t bar_b = smem_u32(smem_raw + RING_BYTES + F1_STAGES * F1_STAGE + (TH / 2) * stg_group_bytes(MD));
+  if (F1_STAGES == 1 && threadIdx.x == 0) {
+    mbar_init(bar_b, NWARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const int tig = threadIdx.x & 127;  // thread index inside the row-pair group
   auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + rp) : "memory"); };
 
@@ -720,8 +735,8 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
   // the data1 rows, 256..511 the new data2 rows.  No register, no scoreboard: DRAM reads overlap the tensor work, and the
   // register loads at the end of the current tile hit L2.
   auto l2_prefetch_tile = [&](const TileGeo& t) {
-    const int tt = threadIdx.x & 255, row = tt >> 5, ch = tt & 31;
-    const bool second = threadIdx.x >= 256;
+    const int tt = threadIdx.x % (NTHREADS / 2), row = tt >> 5, ch = tt & 31;
+    const bool second = threadIdx.x >= NTHREADS / 2;
     const int y = second ? t.y0 + MD + row : t.y0 + row;
     if (ch < C && y < H) {
       const float* p = (second ? d2 : d1) + ((size_t)t.n * C + ch) * plane + (size_t)y * W + t.x0;
@@ -733,16 +748,24 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
   int wr = 0;
   TileGeo cur = geo(0, wr);
   {
-    constexpr int UPRO = (UNITS_F1 + 6 * HR + NWARPS - 1) / NWARPS;   // 8: the whole fresh tile in one batch of loads
-    float e[UPRO][8];
+    constexpr int UALL = UNITS_F1 + 6 * HR;               // units of a fresh tile
+    constexpr int UB = TH == 8 ? 8 : 6;                   // units per warp per batch of loads (registers: 8 floats each)
+    constexpr int NB = (UALL + UB * NWARPS - 1) / (UB * NWARPS);
     if (!(dbg & 32)) {
+#pragma unroll 1
+      for (int b = 0; b < NB; ++b) {
+        float e[UB][8];
+        const int u0 = (b * NWARPS + warp) * UB;
 #pragma unroll
-      for (int k = 0; k < UPRO; ++k) load_unit(cur, warp * UPRO + k, e[k]);
+        for (int k = 0; k < UB; ++k) load_unit(cur, u0 + k, e[k]);
 #pragma unroll
-      for (int k = 0; k < UPRO; ++k) store_unit(cur, warp * UPRO + k, 0, e[k]);
+        for (int k = 0; k < UB; ++k) store_unit(cur, u0 + k, 0, e[k]);
+      }
     }
   }
   __syncthreads();
+  // experiment: de-phase the two co-resident CTAs (dbg >> 16 = delay of the second-wave CTAs in units of 32 ns)
+  if ((dbg >> 16) && blockIdx.x >= kNumSMs) __nanosleep((unsigned)(dbg >> 16) * 32u);
 
   for (int s = 0; s < nStages; ++s) {
     // ---- 1. prefetch the next tile's rows into registers (40 independent 4-byte loads per thread) ----
@@ -771,7 +794,12 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
     for (int rw = 0; rw < 2; ++rw)
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk)
-        ldsm_x4(f1_u32 + (uint32_t)((s & 1) * F1_STAGE + (2 * rp + rw) * F1_ROW_BYTES) + offB[kk], bq[rw][kk]);
+        ldsm_x4(f1_u32 + (uint32_t)((F1_STAGES == 2 ? (s & 1) : 0) * F1_STAGE + (2 * rp + rw) * F1_ROW_BYTES) + offB[kk],
+                bq[rw][kk]);
+    if (F1_STAGES == 1) {   // this warp no longer needs the data1 stage
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_b);
+    }
     const int yA = cur.y0 + 2 * rp;
     float* obase = out + (size_t)cur.n * out_bs + (size_t)yA * W + cur.x0;
     const bool two_k = C > 16;
@@ -888,7 +916,8 @@ __global__ void __launch_bounds__(r4::NTHREADS, 1)
         if (acc0 == 123.456f) out[0] = acc0;
       } else {
         if (dbg & 512) prefetch_next(nxt, pe1, pe2, peh);   // variant: L2-hit loads only at the very end of the tile
-        store_next(nxt, (s + 1) & 1, pe1, pe2, peh);
+        if (F1_STAGES == 1) mbar_wait(bar_b, (uint32_t)(s & 1));
+        store_next(nxt, F1_STAGES == 2 ? ((s + 1) & 1) : 0, pe1, pe2, peh);
       }
     }
     cur = nxt;
@@ -949,42 +978,50 @@ static int launch_mma_impl(const float* d1, const float* d2, float* out, int N, 
                               : (VEC ? "corr_mma_kernel<2,vec>" : "corr_mma_kernel<2,scalar>"));
 }
 
-template <int MD, bool VEC>
+template <int MD, bool VEC, int TH>
 static int launch_mma_ring_impl(const float* d1, const float* d2, float* out, int N, int C, int H, int W,
                                 long long obs, float slope, cudaStream_t st) {
   using namespace r4;
   const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
   const long long tiles = (long long)N * tilesX * tilesY;
-  const int smem = r4::smem_bytes(MD);
+  constexpr int NTHREADS = 64 * TH;
+  const int smem = r4::smem_bytes(MD, TH);
   const int ovec = ((W % 4) == 0 && (obs % 4) == 0 && aligned(out, 16)) ? 1 : 0;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(corr_mma_ring_kernel<MD, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(corr_mma_ring_kernel<MD, VEC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_mma_ring_kernel): %s", cudaGetErrorString(e));
     attr_done = true;
   }
   // strip-aligned work pieces: T = tiles per CTA if all SMs were used; each (n, x-strip) column is cut into
   // ceil(tilesY / T) pieces, one CTA per piece (e.g. level 2 of configs[1]: 64 strips x 2 pieces of 7 tiles = 128 CTAs)
-  const int cap = tuning().corr_grid_cap > 0 ? tuning().corr_grid_cap : kNumSMs;
+  const int cap = tuning().corr_grid_cap > 0 ? tuning().corr_grid_cap : kNumSMs * (TH == 8 ? 1 : 2);
   const long long strips = (long long)N * tilesX;
   const int T = (int)((tiles + cap - 1) / cap);
   int pps = (tilesY + T - 1) / T;
   if (pps < 1) pps = 1;
   if (pps > tilesY) pps = tilesY;
   const unsigned grid = (unsigned)(strips * pps);
-  corr_mma_ring_kernel<MD, VEC><<<grid, NTHREADS, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope, tilesX, tilesY, pps,
+  corr_mma_ring_kernel<MD, VEC, TH><<<grid, NTHREADS, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope, tilesX, tilesY, pps,
                                                               ovec, tuning().corr_dbg);
-  return check_launch(MD == 4 ? (VEC ? "corr_mma_ring_kernel<4,vec>" : "corr_mma_ring_kernel<4,scalar>")
-                              : (VEC ? "corr_mma_ring_kernel<2,vec>" : "corr_mma_ring_kernel<2,scalar>"));
+  if (TH == 8)
+    return check_launch(MD == 4 ? (VEC ? "corr_mma_ring_kernel<4,vec,th8>" : "corr_mma_ring_kernel<4,scalar,th8>")
+                                : (VEC ? "corr_mma_ring_kernel<2,vec,th8>" : "corr_mma_ring_kernel<2,scalar,th8>"));
+  return check_launch(MD == 4 ? (VEC ? "corr_mma_ring_kernel<4,vec,th4>" : "corr_mma_ring_kernel<4,scalar,th4>")
+                              : (VEC ? "corr_mma_ring_kernel<2,vec,th4>" : "corr_mma_ring_kernel<2,scalar,th4>"));
 }
 
 template <int MD>
 static int launch_mma(const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,
                       float slope, cudaStream_t st) {
   const bool vec = (W % 4 == 0) && aligned(d2, 16) && aligned(d1, 16);
-  if (C <= 32 && !tuning().corr_disable_ring)
-    return vec ? launch_mma_ring_impl<MD, true>(d1, d2, out, N, C, H, W, obs, slope, st)
-               : launch_mma_ring_impl<MD, false>(d1, d2, out, N, C, H, W, obs, slope, st);
+  if (C <= 32 && !tuning().corr_disable_ring) {
+    if (tuning().corr_ring_th == 8)
+      return vec ? launch_mma_ring_impl<MD, true, 8>(d1, d2, out, N, C, H, W, obs, slope, st)
+                 : launch_mma_ring_impl<MD, false, 8>(d1, d2, out, N, C, H, W, obs, slope, st);
+    return vec ? launch_mma_ring_impl<MD, true, 4>(d1, d2, out, N, C, H, W, obs, slope, st)
+               : launch_mma_ring_impl<MD, false, 4>(d1, d2, out, N, C, H, W, obs, slope, st);
+  }
   return vec ? launch_mma_impl<MD, true>(d1, d2, out, N, C, H, W, obs, slope, st)
              : launch_mma_impl<MD, false>(d1, d2, out, N, C, H, W, obs, slope, st);
 }

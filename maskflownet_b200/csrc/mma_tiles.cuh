@@ -44,4 +44,12 @@ __host__ __device__ __forceinline__ int swz(int p, int c) { return p * PXB + ((c
 __host__ __device__ constexpr int cout_pad(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : (cout <= 96 ? 96 : 128)); }
 }  // namespace c3
 
+// tcgen05 / TMEM implementation of the same convolution (conv3x3_umma.cu); its weight image follows the mma.sync image
+// inside the packed buffer.  conv3x3_umma_launch returns -1 when the shape does not fit (caller falls back).
+long long conv3x3_sync_packed_bytes(int Cin, int Cout);
+long long conv3x3_umma_packed_bytes(int Cin, int Cout);
+int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int Cout, cudaStream_t st);
+int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
+                        long long out_bs, int N, int Cin, int H, int W, int Cout, int dil, float slope, cudaStream_t st);
+
 }  // namespace mfn

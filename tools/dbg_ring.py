@@ -3,6 +3,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from maskflownet_b200 import ops, _lib
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from kbench import timeit
+import sys as _s
+if len(_s.argv) > 1: _lib.set_tuning("corr_ring_th", int(_s.argv[1]))
 dev="cuda"; N,C,H,W=8,32,112,256
 f1=torch.randn(N,C,H,W,device=dev); f2=torch.randn(N,C,H,W,device=dev); out=torch.empty(N,81,H,W,device=dev)
 flush=torch.empty(256<<20,dtype=torch.uint8,device=dev)
