@@ -203,7 +203,12 @@ MFN_API int mfn_image_warp_concat_forward(const float* im1, const float* im2, co
  * bias + LeakyReLU'ed output channels are written into another slice of (possibly the same) buffer, so the dense block
  * needs no concat copies.  fp32-accurate tensor-core arithmetic (bf16 hi/lo split, 3 MMAs per product, fp32 accumulate).
  * Weights are packed once per layer: mfn_conv3x3_packed_bytes() -> caller allocates -> mfn_conv3x3_pack_weights().
- * Cout <= 128.  leaky_slope = 1 disables the activation.
+ * Cout <= 256.  leaky_slope = 1 disables the activation.
+ * Two kernels serve it: tcgen05.mma with TMEM accumulators (csrc/conv3x3_umma.cu, default; tuning key "conv_umma") and
+ * the mma.sync kernel (csrc/conv3x3.cu, stride 1, Cout <= 128); the packed buffer holds both weight images.
+ * mfn_conv3x3_forward_strided adds stride 2 (pad 1, dilation 1) = the feature pyramid's down-sampling convolutions
+ * conv{L}a / conv{L}x (network/MaskFlownet.py:147-165, 200-201: nn.Conv2D(3x3, strides=2, padding=1) + LeakyReLU);
+ * H, W are the INPUT extents, the output is ((H-1)/stride+1, (W-1)/stride+1).
  * ------------------------------------------------------------------------------------------------- */
 MFN_API long long mfn_conv3x3_packed_bytes(int Cin, int Cout);
 MFN_API int mfn_conv3x3_pack_weights(const float* weight /* (Cout,Cin,3,3) */, void* packed, int Cin, int Cout,
@@ -212,6 +217,9 @@ MFN_API int mfn_conv3x3_forward(const float* x, long long x_batch_stride, const 
                                 float* out, long long out_batch_stride, int N, int Cin, int H, int W, int Cout,
                                 int dilation /* = padding; 1 for the decoder, 2..16 in the context network */,
                                 float leaky_slope, void* stream);
+MFN_API int mfn_conv3x3_forward_strided(const float* x, long long x_batch_stride, const void* packed_weight,
+                                        const float* bias, float* out, long long out_batch_stride, int N, int Cin, int H,
+                                        int W, int Cout, int stride, int dilation, float leaky_slope, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,7 @@ SIGNATURES = {
     "mfn_set_tuning": [ctypes.c_char_p, _i],
     "mfn_conv3x3_pack_weights": [_f, _f, _i, _i, _f],
     "mfn_conv3x3_forward": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _fl, _f],
+    "mfn_conv3x3_forward_strided": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _i, _fl, _f],
 }
 
 
@@ -70,6 +71,11 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = argtypes
             fn.restype = ctypes.c_int
         _lib = L
+        # experiment hook: MFN_TUNING="key=value,key=value" applies mfn_set_tuning at load time
+        for item in filter(None, os.environ.get("MFN_TUNING", "").split(",")):
+            key, _, val = item.partition("=")
+            if L.mfn_set_tuning(key.strip().encode(), int(val)):
+                raise MaskflowError(f"MFN_TUNING: {L.mfn_last_error().decode()}")
     return _lib
 
 

@@ -281,6 +281,7 @@ static int launch_conv(const float* x, long long x_bs, const unsigned char* wpac
 
 // bytes of the mma.sync weight image (first region of the packed buffer; the tcgen05 image follows it)
 long long conv3x3_sync_packed_bytes(int Cin, int Cout) {
+  if (Cout > 128) return 0;   // the mma.sync kernels stop at 128 output channels; wider layers exist only in the tcgen05 image
   return (long long)((Cin + 31) / 32) * 9 * 2 * c3::cout_pad(Cout) * c3::PXB;
 }
 
@@ -296,14 +297,17 @@ extern "C" int mfn_conv3x3_pack_weights(const float* weight, void* packed, int C
   MFN_REQUIRE(weight && packed, MFN_ERR_INVALID_ARG, "mfn_conv3x3_pack_weights: null pointer");
   MFN_REQUIRE(Cin > 0 && Cout > 0, MFN_ERR_INVALID_ARG, "mfn_conv3x3_pack_weights: non-positive extent");
   MFN_REQUIRE(aligned(packed, 16), MFN_ERR_ALIGNMENT, "mfn_conv3x3_pack_weights: packed buffer must be 16-byte aligned");
-  const int CoutP = c3::cout_pad(Cout), nChunks = (Cin + 31) / 32;
-  const long long total = (long long)nChunks * 9 * CoutP * 16;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 4096) blocks = 4096;
-  conv3x3_pack_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(weight, static_cast<unsigned char*>(packed), Cin,
-                                                                       Cout, CoutP, nChunks);
-  const int rc = check_launch("conv3x3_pack_kernel");
-  if (rc) return rc;
+  MFN_REQUIRE(Cout <= 256, MFN_ERR_UNSUPPORTED, "mfn_conv3x3_pack_weights: at most 256 output channels (got %d)", Cout);
+  if (Cout <= 128) {
+    const int CoutP = c3::cout_pad(Cout), nChunks = (Cin + 31) / 32;
+    const long long total = (long long)nChunks * 9 * CoutP * 16;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    conv3x3_pack_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(weight, static_cast<unsigned char*>(packed), Cin,
+                                                                         Cout, CoutP, nChunks);
+    const int rc = check_launch("conv3x3_pack_kernel");
+    if (rc) return rc;
+  }
   return conv3x3_umma_pack(weight, static_cast<unsigned char*>(packed) + conv3x3_sync_packed_bytes(Cin, Cout), Cin, Cout,
                            as_stream(stream));
 }
@@ -311,23 +315,37 @@ extern "C" int mfn_conv3x3_pack_weights(const float* weight, void* packed, int C
 extern "C" int mfn_conv3x3_forward(const float* x, long long x_batch_stride, const void* packed_weight,
                                    const float* bias, float* out, long long out_batch_stride, int N, int Cin, int H,
                                    int W, int Cout, int dilation, float leaky_slope, void* stream) {
+  return mfn_conv3x3_forward_strided(x, x_batch_stride, packed_weight, bias, out, out_batch_stride, N, Cin, H, W, Cout, 1,
+                                     dilation, leaky_slope, stream);
+}
+
+extern "C" int mfn_conv3x3_forward_strided(const float* x, long long x_batch_stride, const void* packed_weight,
+                                           const float* bias, float* out, long long out_batch_stride, int N, int Cin,
+                                           int H, int W, int Cout, int stride, int dilation, float leaky_slope,
+                                           void* stream) {
   using namespace mfn;
   MFN_REQUIRE(x && packed_weight && out, MFN_ERR_INVALID_ARG, "mfn_conv3x3_forward: null pointer");
   MFN_REQUIRE(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, MFN_ERR_INVALID_ARG,
               "mfn_conv3x3_forward: non-positive extent");
-  MFN_REQUIRE(Cout <= 128, MFN_ERR_UNSUPPORTED, "mfn_conv3x3_forward: at most 128 output channels (got %d)", Cout);
+  MFN_REQUIRE(Cout <= 256, MFN_ERR_UNSUPPORTED, "mfn_conv3x3_forward: at most 256 output channels (got %d)", Cout);
   MFN_REQUIRE(dilation >= 1, MFN_ERR_INVALID_ARG, "mfn_conv3x3_forward: dilation must be >= 1");
+  MFN_REQUIRE(stride == 1 || (stride == 2 && dilation == 1), MFN_ERR_UNSUPPORTED,
+              "mfn_conv3x3_forward: stride must be 1, or 2 with dilation 1 (got stride %d, dilation %d)", stride, dilation);
   MFN_REQUIRE(aligned(packed_weight, 16), MFN_ERR_ALIGNMENT, "mfn_conv3x3_forward: packed weights must be 16-byte aligned");
+  const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
   const long long xbs = x_batch_stride ? x_batch_stride : (long long)Cin * H * W;
-  const long long obs = out_batch_stride ? out_batch_stride : (long long)Cout * H * W;
-  MFN_REQUIRE(xbs >= (long long)Cin * H * W && obs >= (long long)Cout * H * W, MFN_ERR_INVALID_ARG,
+  const long long obs = out_batch_stride ? out_batch_stride : (long long)Cout * OH * OW;
+  MFN_REQUIRE(xbs >= (long long)Cin * H * W && obs >= (long long)Cout * OH * OW, MFN_ERR_INVALID_ARG,
               "mfn_conv3x3_forward: batch stride smaller than the tensor");
   const unsigned char* wp = static_cast<const unsigned char*>(packed_weight);
   cudaStream_t st = as_stream(stream);
-  if (tuning().conv_umma && W >= tuning().conv_umma_min_w) {   // tcgen05 / TMEM kernel
+  const bool sync_ok = Cout <= 128 && stride == 1;   // shapes the mma.sync kernels cover
+  if ((tuning().conv_umma && W >= tuning().conv_umma_min_w) || !sync_ok) {   // tcgen05 / TMEM kernel
     const int rc = conv3x3_umma_launch(x, xbs, wp + conv3x3_sync_packed_bytes(Cin, Cout), bias, out, obs, N, Cin, H, W,
-                                       Cout, dilation, leaky_slope, st);
+                                       Cout, stride, dilation, leaky_slope, st);
     if (rc != -1) return rc;
+    MFN_REQUIRE(sync_ok, MFN_ERR_UNSUPPORTED, "mfn_conv3x3_forward: shape fits neither kernel (Cout=%d stride=%d dilation=%d)",
+                Cout, stride, dilation);
   }
   const int nt = (Cout + 7) / 8;   // n8 tiles needed
   if (nt <= 4) return launch_conv<1, 4>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, st);

@@ -32,11 +32,28 @@ constexpr int NPROD = 6;         // producer warps (warps 2..7); warps 4..7 doub
 constexpr int WSTAGES = 4;
 constexpr int BATCH = 4;         // producer items (32 entries x 8 channels) in flight per warp
 
-__host__ __device__ inline int n_slots(int dil) { return dil >= R ? 3 * R : R + 2 * dil; }
-__host__ __device__ inline int slot_of(int r, int ky, int dil) { return dil >= R ? ky * R + r : r + ky * dil; }
-__host__ __device__ inline int row_of_slot(int slot, int y0, int dil) {
-  return dil >= R ? y0 + (slot % R) + (slot / R - 1) * dil : y0 - dil + slot;
+// Geometry of the converted input tile: `nslots` image rows of PW entries each.
+//   stride 1 (any dilation d): rows y0 - d .. y0 + R - 1 + d (or the 3R rows the taps touch when d >= R); entry p of a row is
+//     pixel x0 - d + p; tap (ky, kx) of output row r starts at entry slot(r, ky) * PW + kx * d.
+//   stride 2 (d = 1): rows 2 y0 - 1 .. 2 y0 + 2R - 1; a row is de-interleaved into its even pixels 2 (x0 + p), p < 128, and
+//     its odd pixels 2 (x0 - 1 + p - 128) + 1, p >= 128, so that "next output pixel" is again "next entry": tap kx reads
+//     the odd block from 0 (kx = 0), the even block (kx = 1) or the odd block from 1 (kx = 2).
+__host__ __device__ inline int n_slots(int stride, int dil) { return stride == 2 ? 2 * R + 1 : (dil >= R ? 3 * R : R + 2 * dil); }
+__host__ __device__ inline int row_pitch(int stride, int dil) { return stride == 2 ? 2 * MT + 1 : MT + 2 * dil; }
+__host__ __device__ inline int slot_of(int r, int ky, int stride, int dil) {
+  return stride == 2 ? 2 * r + ky : (dil >= R ? ky * R + r : r + ky * dil);
 }
+__host__ __device__ inline int tap_xoff(int kx, int stride, int dil) {
+  return stride == 2 ? (kx == 1 ? 0 : (kx == 0 ? MT : MT + 1)) : kx * dil;
+}
+__host__ __device__ inline int row_of_slot(int slot, int y0, int stride, int dil) {
+  return stride == 2 ? 2 * y0 - 1 + slot : (dil >= R ? y0 + (slot % R) + (slot / R - 1) * dil : y0 - dil + slot);
+}
+__host__ __device__ inline int x_of_entry(int p, int x0, int stride, int dil) {
+  return stride == 2 ? (p < MT ? 2 * (x0 + p) : 2 * (x0 - 1 + p - MT) + 1) : x0 - dil + p;
+}
+// output channels padded to the MMA's N granularity
+__host__ __device__ inline int cout_pad(int cout) { return cout <= 16 ? 16 : (cout + 15) / 16 * 16; }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -79,14 +96,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
-      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -134,10 +148,11 @@ __global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned c
 __global__ void __launch_bounds__(um::NTHREADS, 2)
     conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
                         const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
-                        int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int dil, int tmem_cols) {
+                        int OH, int OW, int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int stride,
+                        int dil, int tmem_cols) {
   using namespace um;
   extern __shared__ __align__(128) unsigned char smem[];
-  const int nslots = n_slots(dil), PW = MT + 2 * dil, E = nslots * PW;
+  const int nslots = n_slots(stride, dil), PW = row_pitch(stride, dil), E = nslots * PW;
   const SmemMap sm = smem_map(E, CoutP);
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + sm.bar_off;
@@ -149,7 +164,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 2)
   const int tile = blockIdx.x;
   const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
   const int x0 = tx * MT, y0 = ty * R;
-  const size_t plane = (size_t)H * W;
+  const size_t plane = (size_t)H * W, oplane = (size_t)OH * OW;
   const int nIter = nChunks * 9;
 
   if (tid == 0) {
@@ -194,7 +209,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 2)
           const uint64_t b_hi = smem_desc(w_st, b_lbo, 128), b_lo = smem_desc(w_st + (uint32_t)(sm.w_tile / 2), b_lbo, 128);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const uint32_t a_addr = a_st + (uint32_t)((slot_of(r, ky, dil) * PW + kx * dil) * 16);
+            const uint32_t a_addr = a_st + (uint32_t)((slot_of(r, ky, stride, dil) * PW + tap_xoff(kx, stride, dil)) * 16);
             const uint64_t a_hi = smem_desc(a_addr, a_lbo, 128), a_lo = smem_desc(a_addr + (uint32_t)sm.a_lo, a_lbo, 128);
             const uint32_t d = tmem_base + (uint32_t)(r * CoutP);
             umma_bf16(d, a_hi, b_lo, idesc, it > 0 ? 1u : 0u);
@@ -233,7 +248,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 2)
           const int t = k0 + b * NPROD;
           const int kc = t & 1, e = (t >> 1) * 32 + lane;
           const int slot = e / PW, p = e - slot * PW;
-          const int y = row_of_slot(slot, y0, dil), xx = x0 - dil + p;
+          const int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(p, x0, stride, dil);
           const bool ok = t < nItems && e < E && y >= 0 && y < H && xx >= 0 && xx < W;
           const int c0 = 16 * c + 8 * kc;
           const float* src = xn + (size_t)c0 * plane + (size_t)(ok ? y : 0) * W + (ok ? xx : 0);
@@ -272,19 +287,19 @@ __global__ void __launch_bounds__(um::NTHREADS, 2)
 #pragma unroll 1
       for (int r = 0; r < R; ++r) {
         const int y = y0 + r;
-        float* on = out + (size_t)n * out_bs + (size_t)y * W + xx;
-        const bool okp = y < H && xx < W;
+        float* on = out + (size_t)n * out_bs + (size_t)y * OW + xx;
+        const bool okp = y < OH && xx < OW;
 #pragma unroll 1
-        for (int nc = 0; nc < CoutP / 32; ++nc) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(r * CoutP + nc * 32), v);
+        for (int nc = 0; nc < CoutP / 16; ++nc) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(r * CoutP + nc * 16), v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int f = nc * 32 + j;
+          for (int j = 0; j < 16; ++j) {
+            const int f = nc * 16 + j;
             if (f < Cout && okp) {
               const float b = bias ? __ldg(bias + f) : 0.f;
-              on[(size_t)f * plane] = leaky(__uint_as_float(v[j]) + b, slope);
+              on[(size_t)f * oplane] = leaky(__uint_as_float(v[j]) + b, slope);
             }
           }
         }
@@ -300,11 +315,11 @@ __global__ void __launch_bounds__(um::NTHREADS, 2)
 
 // ---------------------------------------------------------------------------------------------------------
 long long conv3x3_umma_packed_bytes(int Cin, int Cout) {
-  return (long long)((Cin + 15) / 16) * 9 * 64 * c3::cout_pad(Cout);
+  return (long long)((Cin + 15) / 16) * 9 * 64 * um::cout_pad(Cout);
 }
 
 int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int Cout, cudaStream_t st) {
-  const int CoutP = c3::cout_pad(Cout), nChunks16 = (Cin + 15) / 16;
+  const int CoutP = um::cout_pad(Cout), nChunks16 = (Cin + 15) / 16;
   const long long total = (long long)nChunks16 * 9 * CoutP * 8;
   long long blocks = (total + 255) / 256;
   if (blocks > 4096) blocks = 4096;
@@ -314,12 +329,15 @@ int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int C
 
 // returns -1 when the shape does not fit this kernel (caller falls back to the mma.sync kernel)
 int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
-                        long long out_bs, int N, int Cin, int H, int W, int Cout, int dil, float slope, cudaStream_t st) {
+                        long long out_bs, int N, int Cin, int H, int W, int Cout, int stride, int dil, float slope,
+                        cudaStream_t st) {
   using namespace um;
-  const int CoutP = c3::cout_pad(Cout), nChunks = (Cin + 15) / 16;
-  const int E = n_slots(dil) * (MT + 2 * dil);
+  if (Cout > 256 || (stride != 1 && !(stride == 2 && dil == 1))) return -1;
+  const int CoutP = um::cout_pad(Cout), nChunks = (Cin + 15) / 16;
+  const int E = n_slots(stride, dil) * row_pitch(stride, dil);
   const SmemMap sm = smem_map(E, CoutP);
   if (sm.total > 227 * 1024 || E * 16 > 0x3FFF * 16) return -1;
+  const int OH = stride == 2 ? (H - 1) / 2 + 1 : H, OW = stride == 2 ? (W - 1) / 2 + 1 : W;
   static int configured = 0;
   if (configured < sm.total) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
@@ -328,10 +346,10 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   }
   int cols = 32;
   while (cols < R * CoutP) cols *= 2;
-  const int tilesX = (W + MT - 1) / MT, tilesY = (H + R - 1) / R;
+  const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
   const unsigned grid = (unsigned)((long long)N * tilesX * tilesY);
-  conv3x3_umma_kernel<<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, Cout, CoutP, nChunks,
-                                                        slope, tilesX, tilesY, dil, cols);
+  conv3x3_umma_kernel<<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout, CoutP,
+                                                        nChunks, slope, tilesX, tilesY, stride, dil, cols);
   return check_launch("conv3x3_umma_kernel");
 }
 

@@ -82,12 +82,28 @@ class _FlowNetBase(nn.Module):
         return self.use_tc_conv and x.is_cuda and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
 
     def _pyramid(self, x, names):
+        """Six levels of (3x3 stride-2, 3x3, 3x3) convolutions + LeakyReLU (network/MaskFlownet.py:200-202).  Inference:
+        all eighteen run on the tcgen05 convolution kernel (bias + activation fused)."""
         feats = []
+        fast = self._fast(x)
         for lvl in range(1, 7):
-            for sfx in names:
-                x = tF.leaky_relu(getattr(self, f"conv{lvl}{sfx}")(x), SLOPE)
+            for j, sfx in enumerate(names):
+                name = f"conv{lvl}{sfx}"
+                conv = getattr(self, name)
+                if fast:
+                    x = ops.conv3x3(x, self._packed(name), conv.bias, conv.out_channels, SLOPE, 1, 2 if j == 0 else 1)
+                else:
+                    x = tF.leaky_relu(conv(x), SLOPE)
             feats.append(x)
         return feats  # [c?1 .. c?6]
+
+    def _pyramid_pair(self, im1, im2, names):
+        """Both images through the shared pyramid; inference batches them into one pass (half the launches)."""
+        if self._fast(im1):
+            n = im1.shape[0]
+            f = self._pyramid(torch.cat([im1, im2], dim=0), names)
+            return [t[:n] for t in f], [t[n:] for t in f]
+        return self._pyramid(im1, names), self._pyramid(im2, names)
 
     def _dense(self, lvl, x):
         """x = concat(leaky(conv_i(x)), x) five times (network/MaskFlownet.py:219-223 ...).  Inference: one pre-allocated
@@ -198,8 +214,7 @@ class MaskFlownetS(_FlowNetBase):
     def forward(self, im1: torch.Tensor, im2: torch.Tensor, want_cascade_inputs: bool = False):
         """Returns (predictions [flow6..flow2, each * scale], [sigmoid(mask2)], srcs or None) like the reference
         (network/MaskFlownet.py:302-315).  srcs (needed only by the cascade) is built when want_cascade_inputs."""
-        c1 = self._pyramid(im1, "abc")
-        c2 = self._pyramid(im2, "abc")
+        c1, c2 = self._pyramid_pair(im1, im2, "abc")
         x = self._corr_block(6, c1[5], c2[5], [])   # correlation + dense block
         flow = self.pred_flow6(x)
         mask = self.pred_mask6(x)

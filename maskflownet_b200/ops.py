@@ -374,14 +374,17 @@ def conv3x3_pack(weight: torch.Tensor) -> torch.Tensor:
 
 
 def conv3x3_slices(buf_in: torch.Tensor, c_in0: int, Cin: int, packed: torch.Tensor, bias: Optional[torch.Tensor],
-                   buf_out: torch.Tensor, c_out0: int, Cout: int, leaky_slope: float = 0.1, dilation: int = 1) -> None:
+                   buf_out: torch.Tensor, c_out0: int, Cout: int, leaky_slope: float = 0.1, dilation: int = 1,
+                   stride: int = 1) -> None:
     """out = LeakyReLU(conv3x3(buf_in[:, c_in0:c_in0+Cin]) + bias) written to buf_out[:, c_out0:c_out0+Cout]; both buffers
-    dense NCHW (they may be the same tensor: the dense block's concat buffer).  Inference only (no autograd)."""
+    dense NCHW (they may be the same tensor: the dense block's concat buffer).  stride 2 (pad 1) = the pyramid's
+    down-sampling convolutions: buf_out is then ((H-1)//2+1, (W-1)//2+1).  Inference only (no autograd)."""
     for t, nm in ((buf_in, "buf_in"), (buf_out, "buf_out")):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4):
             raise MaskflowError(f"conv3x3_slices: {nm} must be a contiguous CUDA float32 NCHW tensor")
     N, Cti, H, W = buf_in.shape
-    if buf_out.shape[0] != N or buf_out.shape[2:] != (H, W):
+    OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if buf_out.shape[0] != N or tuple(buf_out.shape[2:]) != (OH, OW):
         raise MaskflowError("conv3x3_slices: buffers disagree in N/H/W")
     Cto = buf_out.shape[1]
     if not (0 <= c_in0 and c_in0 + Cin <= Cti and 0 <= c_out0 and c_out0 + Cout <= Cto):
@@ -389,17 +392,17 @@ def conv3x3_slices(buf_in: torch.Tensor, c_in0: int, Cin: int, packed: torch.Ten
     if buf_in.data_ptr() == buf_out.data_ptr() and not (c_out0 + Cout <= c_in0 or c_in0 + Cin <= c_out0):
         raise MaskflowError("conv3x3_slices: input and output slices overlap")
     b = _chk(bias, "conv3x3_slices.bias", optional=True)
-    plane = H * W
-    xin = ctypes.c_void_p(buf_in.data_ptr() + 4 * c_in0 * plane)
-    xout = ctypes.c_void_p(buf_out.data_ptr() + 4 * c_out0 * plane)
-    _call("mfn_conv3x3_forward", buf_in.device, xin, Cti * plane, _p(packed), _p(b), xout, Cto * plane, N, Cin, H, W, Cout,
-          int(dilation), float(leaky_slope))
+    xin = ctypes.c_void_p(buf_in.data_ptr() + 4 * c_in0 * H * W)
+    xout = ctypes.c_void_p(buf_out.data_ptr() + 4 * c_out0 * OH * OW)
+    _call("mfn_conv3x3_forward_strided", buf_in.device, xin, Cti * H * W, _p(packed), _p(b), xout, Cto * OH * OW, N, Cin, H, W,
+          Cout, int(stride), int(dilation), float(leaky_slope))
 
 
 def conv3x3(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], Cout: int, leaky_slope: float = 0.1,
-            dilation: int = 1):
-    """3x3 convolution, stride 1, padding = dilation (the decoder / context-network convolutions), + LeakyReLU."""
+            dilation: int = 1, stride: int = 1):
+    """3x3 convolution, padding = dilation, stride 1 (decoder / context network) or 2 (pyramid), + LeakyReLU."""
     x = _chk(x, "conv3x3.x")
-    out = torch.empty((x.shape[0], Cout, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
-    conv3x3_slices(x, 0, x.shape[1], packed, bias, out, 0, Cout, leaky_slope, dilation)
+    out = torch.empty((x.shape[0], Cout, (x.shape[2] - 1) // stride + 1, (x.shape[3] - 1) // stride + 1), device=x.device,
+                      dtype=torch.float32)
+    conv3x3_slices(x, 0, x.shape[1], packed, bias, out, 0, Cout, leaky_slope, dilation, stride)
     return out

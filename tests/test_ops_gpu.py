@@ -382,6 +382,52 @@ def test_conv3x3_dilated(dil):
     assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max()))
 
 
+@pytest.mark.parametrize("umma", [1, 0])
+@pytest.mark.parametrize("N,Cin,Cout,H,W,dil", [(1, 16, 32, 4, 128, 1), (1, 32, 64, 5, 130, 1), (1, 64, 96, 9, 256, 1),
+                                                (2, 131, 128, 12, 40, 1), (1, 40, 96, 21, 45, 2), (1, 40, 64, 21, 45, 16),
+                                                (1, 128, 128, 30, 200, 8), (1, 20, 2, 9, 140, 1), (1, 33, 16, 6, 70, 1)])
+def test_conv3x3_tcgen05_and_mma_sync_agree_with_fp64(N, Cin, Cout, H, W, dil, umma):
+    """Both kernels behind mfn_conv3x3_forward (tcgen05/TMEM and mma.sync) against a float64 convolution, incl. tiles that
+    straddle the 128-pixel M tile, the image border, channel-chunk padding and N padding."""
+    rng = np.random.default_rng(41)
+    x = feat(rng, (N, Cin, H, W))
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(),
+                                     torch.from_numpy(b).double(), padding=dil, dilation=dil)
+    ref = torch.nn.functional.leaky_relu(ref, 0.1).float().numpy()
+    _lib.set_tuning("conv_umma", umma)
+    try:
+        got = ops.conv3x3(cu(x), ops.conv3x3_pack(cu(w)), cu(b), Cout, 0.1, dilation=dil).cpu().numpy()
+        kern = _lib.last_kernel()
+    finally:
+        _lib.set_tuning("conv_umma", 1)
+    assert ("umma" in kern) == bool(umma), kern
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max())), kern
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 3, 16, 64, 128), (1, 16, 32, 30, 258), (1, 32, 64, 17, 37), (1, 96, 128, 9, 20),
+                                            (1, 128, 196, 6, 12), (1, 4, 16, 5, 7)])
+def test_conv3x3_stride2_pyramid(N, Cin, Cout, H, W):
+    """conv{L}a / conv{L}x of the feature pyramid: 3x3, stride 2, pad 1 (network/MaskFlownet.py:147-165), odd and even
+    extents, and the 196-channel level-6 layer (wider than one mma.sync CTA covers: tcgen05 image only)."""
+    rng = np.random.default_rng(43)
+    x = feat(rng, (N, Cin, H, W))
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(),
+                                     torch.from_numpy(b).double(), stride=2, padding=1)
+    ref = torch.nn.functional.leaky_relu(ref, 0.1).float().numpy()
+    got = ops.conv3x3(cu(x), ops.conv3x3_pack(cu(w)), cu(b), Cout, 0.1, stride=2).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max())), _lib.last_kernel()
+    # the same layer at stride 1 (196 outputs exist only in the tcgen05 weight image)
+    ref1 = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(
+        torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=1), 0.1).float().numpy()
+    got1 = ops.conv3x3(cu(x), ops.conv3x3_pack(cu(w)), cu(b), Cout, 0.1).cpu().numpy()
+    assert np.abs(got1 - ref1).max() <= 1e-4 * max(1.0, float(np.abs(ref1).max())), _lib.last_kernel()
+
+
 def test_conv3x3_in_place_concat_block():
     """The dense block: five convolutions reading / writing channel slices of one buffer == torch.cat chain."""
     rng = np.random.default_rng(32)

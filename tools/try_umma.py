@@ -25,14 +25,15 @@ for shp in [(1, 16, 32, 4, 128), (1, 16, 128, 2, 128), (1, 32, 64, 5, 130), (2, 
             (1, 579, 128, 10, 24), (1, 64, 96, 9, 256), (1, 40, 96, 21, 45, 2), (1, 40, 96, 21, 45, 4), (1, 40, 64, 21, 45, 16), (1, 128, 128, 30, 200, 8)]:
     check(*shp)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for (N, Cin, Cout, H, W, dil) in [(8, 131, 128, 112, 256, 1), (8, 565, 32, 112, 256, 1), (8, 259, 128, 56, 128, 1), (8, 128, 128, 112, 256, 2),
-                                  (8, 128, 96, 112, 256, 8), (8, 96, 64, 112, 256, 16), (8, 341, 128, 28, 64, 1), (8, 405, 128, 14, 32, 1)]:
+for (N, Cin, Cout, H, W, stride) in [(16, 3, 16, 448, 1024, 2), (16, 16, 16, 224, 512, 1), (16, 16, 32, 224, 512, 2), (16, 32, 32, 112, 256, 1),
+                                     (16, 32, 64, 112, 256, 2), (16, 64, 64, 56, 128, 1), (16, 64, 96, 56, 128, 2), (16, 96, 96, 28, 64, 1),
+                                     (16, 96, 128, 28, 64, 2), (16, 128, 128, 14, 32, 1), (16, 128, 196, 14, 32, 2), (16, 196, 196, 7, 16, 1),
+                                     (8, 597, 2, 112, 256, 1), (8, 16, 32, 112, 256, 1)]:
     x = torch.randn(N, Cin, H, W, device=dev); w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05; b = torch.randn(Cout, device=dev)
-    packed = ops.conv3x3_pack(w); out = torch.empty(N, Cout, H, W, device=dev)
-    line = f"N={N} Cin={Cin} Cout={Cout} {H}x{W} dil={dil}:"
-    for mode in (1, 0):
-        _lib.set_tuning("conv_umma", mode); _lib.set_tuning("conv_umma_min_w", 1)
-        avg, best = timeit(lambda: ops.conv3x3_slices(x, 0, Cin, packed, b, out, 0, Cout, 0.1, dilation=dil), 10, flush)
-        tf = 2.0 * N * H * W * 9 * Cin * Cout / (avg * 1e-3) / 1e12
-        line += f"  {'umma' if mode else 'sync'} {avg*1e3:8.1f} us ({tf:6.1f} TFLOP/s fp32-equiv)"
-    print(line, flush=True)
+    packed = ops.conv3x3_pack(w); OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty(N, Cout, OH, OW, device=dev)
+    avg, best = timeit(lambda: ops.conv3x3_slices(x, 0, Cin, packed, b, out, 0, Cout, 0.1, 1, stride), 10, flush)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cudnn.benchmark = True
+    avg2, best2 = timeit(lambda: torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, w, b, stride=stride, padding=1), 0.1), 10, flush)
+    mb = 4 * (x.numel() + out.numel()) / 1e6
+    print(f"N={N} {Cin}->{Cout} {H}x{W} s{stride}: umma {avg*1e3:8.1f} us ({mb/avg/1e3:6.1f} GB/s alg)   cuDNN+leaky {avg2*1e3:8.1f} us", flush=True)
