@@ -206,9 +206,13 @@ MFN_API int mfn_image_warp_concat_forward(const float* im1, const float* im2, co
  * Cout <= 256.  leaky_slope = 1 disables the activation.
  * Two kernels serve it: tcgen05.mma with TMEM accumulators (csrc/conv3x3_umma.cu, default; tuning key "conv_umma") and
  * the mma.sync kernel (csrc/conv3x3.cu, stride 1, Cout <= 128); the packed buffer holds both weight images.
- * mfn_conv3x3_forward_strided adds stride 2 (pad 1, dilation 1) = the feature pyramid's down-sampling convolutions
- * conv{L}a / conv{L}x (network/MaskFlownet.py:147-165, 200-201: nn.Conv2D(3x3, strides=2, padding=1) + LeakyReLU);
- * H, W are the INPUT extents, the output is ((H-1)/stride+1, (W-1)/stride+1).
+ * mfn_conv3x3_forward_ex adds
+ *   - stride 2 (pad 1, dilation 1) = the feature pyramid's down-sampling convolutions conv{L}a / conv{L}x
+ *     (network/MaskFlownet.py:147-165, 200-201: nn.Conv2D(3x3, strides=2, padding=1) + LeakyReLU); H, W are the INPUT
+ *     extents, the output is ((H-1)/stride+1, (W-1)/stride+1);
+ *   - out_mode MFN_CONV_OUT_DEPTH_TO_SPACE2: conv channel (2 py + px) * F + f is written to out[n][f][2y+py][2x+px]
+ *     (F = Cout / 4, bias has F entries, out is (N, F, 2H, 2W)).  With the weight re-arrangement of INTEGRATION.md this
+ *     is the decoder's nn.Conv2DTranspose(kernel 4, stride 2, pad 1) `upfeat` layers (network/MaskFlownet.py:225, 243 ...).
  * ------------------------------------------------------------------------------------------------- */
 MFN_API long long mfn_conv3x3_packed_bytes(int Cin, int Cout);
 MFN_API int mfn_conv3x3_pack_weights(const float* weight /* (Cout,Cin,3,3) */, void* packed, int Cin, int Cout,
@@ -217,9 +221,11 @@ MFN_API int mfn_conv3x3_forward(const float* x, long long x_batch_stride, const 
                                 float* out, long long out_batch_stride, int N, int Cin, int H, int W, int Cout,
                                 int dilation /* = padding; 1 for the decoder, 2..16 in the context network */,
                                 float leaky_slope, void* stream);
-MFN_API int mfn_conv3x3_forward_strided(const float* x, long long x_batch_stride, const void* packed_weight,
-                                        const float* bias, float* out, long long out_batch_stride, int N, int Cin, int H,
-                                        int W, int Cout, int stride, int dilation, float leaky_slope, void* stream);
+#define MFN_CONV_OUT_NCHW 0
+#define MFN_CONV_OUT_DEPTH_TO_SPACE2 1
+MFN_API int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, const void* packed_weight, const float* bias,
+                                   float* out, long long out_batch_stride, int N, int Cin, int H, int W, int Cout,
+                                   int stride, int dilation, int out_mode, float leaky_slope, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ SIGNATURES = {
     "mfn_set_tuning": [ctypes.c_char_p, _i],
     "mfn_conv3x3_pack_weights": [_f, _f, _i, _i, _f],
     "mfn_conv3x3_forward": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _fl, _f],
-    "mfn_conv3x3_forward_strided": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _i, _fl, _f],
+    "mfn_conv3x3_forward_ex": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _f],
 }
 
 

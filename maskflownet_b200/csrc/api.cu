@@ -51,6 +51,7 @@ extern "C" int mfn_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "corr_dbg")) mfn::tuning().corr_dbg = value;
   else if (!strcmp(key, "corr_ring_th")) mfn::tuning().corr_ring_th = value;
   else if (!strcmp(key, "conv_umma")) mfn::tuning().conv_umma = value;
+  else if (!strcmp(key, "conv_grid_cap")) mfn::tuning().conv_grid_cap = value;
   else if (!strcmp(key, "conv_umma_min_w")) mfn::tuning().conv_umma_min_w = value;
   else return mfn::fail(MFN_ERR_INVALID_ARG, "mfn_set_tuning: unknown key '%s'", key);
   return MFN_OK;

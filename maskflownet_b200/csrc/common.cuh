@@ -17,6 +17,7 @@ struct Tuning {
   int corr_grid_cap = 0;      // > 0: cap the persistent grid of the MMA correlation kernels (tests force long tile runs)
   int corr_disable_ring = 0;  // 1: use the tile kernel even for C <= 32
   int conv_umma = 1;          // 1: 3x3 convolutions run on tcgen05 / TMEM (conv3x3_umma.cu), 0: mma.sync kernel
+  int conv_grid_cap = 0;      // persistent tcgen05 convolution: CTAs (0 = one per SM); tests force long per-CTA tile runs
   int conv_umma_min_w = 1;    // narrower images stay on the mma.sync kernel (a 128-pixel M tile would be mostly padding)
   int corr_ring_th = 8;       // tile height of the strip-marching kernel: 4 (8 warps, 2 CTAs/SM) or 8 (16 warps, 1 CTA/SM)
   int corr_dbg = 0;           // profiling aid for the ring kernel: 2 = producers idle, 4 = no epilogue, 8 = no MMA (results invalid)

@@ -315,14 +315,14 @@ extern "C" int mfn_conv3x3_pack_weights(const float* weight, void* packed, int C
 extern "C" int mfn_conv3x3_forward(const float* x, long long x_batch_stride, const void* packed_weight,
                                    const float* bias, float* out, long long out_batch_stride, int N, int Cin, int H,
                                    int W, int Cout, int dilation, float leaky_slope, void* stream) {
-  return mfn_conv3x3_forward_strided(x, x_batch_stride, packed_weight, bias, out, out_batch_stride, N, Cin, H, W, Cout, 1,
-                                     dilation, leaky_slope, stream);
+  return mfn_conv3x3_forward_ex(x, x_batch_stride, packed_weight, bias, out, out_batch_stride, N, Cin, H, W, Cout, 1,
+                                dilation, MFN_CONV_OUT_NCHW, leaky_slope, stream);
 }
 
-extern "C" int mfn_conv3x3_forward_strided(const float* x, long long x_batch_stride, const void* packed_weight,
-                                           const float* bias, float* out, long long out_batch_stride, int N, int Cin,
-                                           int H, int W, int Cout, int stride, int dilation, float leaky_slope,
-                                           void* stream) {
+extern "C" int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, const void* packed_weight,
+                                      const float* bias, float* out, long long out_batch_stride, int N, int Cin, int H,
+                                      int W, int Cout, int stride, int dilation, int out_mode, float leaky_slope,
+                                      void* stream) {
   using namespace mfn;
   MFN_REQUIRE(x && packed_weight && out, MFN_ERR_INVALID_ARG, "mfn_conv3x3_forward: null pointer");
   MFN_REQUIRE(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, MFN_ERR_INVALID_ARG,
@@ -332,6 +332,8 @@ extern "C" int mfn_conv3x3_forward_strided(const float* x, long long x_batch_str
   MFN_REQUIRE(stride == 1 || (stride == 2 && dilation == 1), MFN_ERR_UNSUPPORTED,
               "mfn_conv3x3_forward: stride must be 1, or 2 with dilation 1 (got stride %d, dilation %d)", stride, dilation);
   MFN_REQUIRE(aligned(packed_weight, 16), MFN_ERR_ALIGNMENT, "mfn_conv3x3_forward: packed weights must be 16-byte aligned");
+  MFN_REQUIRE(out_mode == MFN_CONV_OUT_NCHW || (out_mode == MFN_CONV_OUT_DEPTH_TO_SPACE2 && stride == 1 && Cout % 4 == 0),
+              MFN_ERR_INVALID_ARG, "mfn_conv3x3_forward: depth-to-space output needs stride 1 and Cout %% 4 == 0");
   const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
   const long long xbs = x_batch_stride ? x_batch_stride : (long long)Cin * H * W;
   const long long obs = out_batch_stride ? out_batch_stride : (long long)Cout * OH * OW;
@@ -339,10 +341,10 @@ extern "C" int mfn_conv3x3_forward_strided(const float* x, long long x_batch_str
               "mfn_conv3x3_forward: batch stride smaller than the tensor");
   const unsigned char* wp = static_cast<const unsigned char*>(packed_weight);
   cudaStream_t st = as_stream(stream);
-  const bool sync_ok = Cout <= 128 && stride == 1;   // shapes the mma.sync kernels cover
+  const bool sync_ok = Cout <= 128 && stride == 1 && out_mode == MFN_CONV_OUT_NCHW;   // what the mma.sync kernels cover
   if ((tuning().conv_umma && W >= tuning().conv_umma_min_w) || !sync_ok) {   // tcgen05 / TMEM kernel
     const int rc = conv3x3_umma_launch(x, xbs, wp + conv3x3_sync_packed_bytes(Cin, Cout), bias, out, obs, N, Cin, H, W,
-                                       Cout, stride, dilation, leaky_slope, st);
+                                       Cout, stride, dilation, out_mode, leaky_slope, st);
     if (rc != -1) return rc;
     MFN_REQUIRE(sync_ok, MFN_ERR_UNSUPPORTED, "mfn_conv3x3_forward: shape fits neither kernel (Cout=%d stride=%d dilation=%d)",
                 Cout, stride, dilation);

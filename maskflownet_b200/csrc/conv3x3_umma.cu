@@ -1,23 +1,25 @@
-// conv3x3_umma.cu -- the decoder / context-network 3x3 convolution on the 5th-generation
-// tensor cores: tcgen05.mma with the accumulators in tensor memory (TMEM).  Same contract as conv3x3.cu (channel slices of
-// a level buffer in, bias + LeakyReLU'ed channel slice out, fp32-accurate through the bf16 hi/lo split: three MMAs
-// hi*lo + lo*hi + hi*hi per product), reference call sites network/MaskFlownet.py:203-300.
+// conv3x3_umma.cu -- the 3x3 convolutions of the decoder, the context network and the feature pyramid (SURVEY.md section
+// 8f, row N2) on the 5th-generation tensor cores: tcgen05.mma with the accumulators in tensor memory (TMEM).  Contract as in
+// conv3x3.cu (channel slices of a level buffer in, bias + LeakyReLU'ed channel slice out, fp32-accurate through the bf16
+// hi/lo split: three MMAs hi*lo + lo*hi + hi*hi per product); reference call sites network/MaskFlownet.py:147-300.
 //
 // Implicit GEMM without im2col:   D[pixel, f] = sum_{tap, c} X[pixel + tap offset, c] * Wt[tap][c][f]
-//   * M tile = 128 consecutive pixels of one image row, a CTA owns R = 2 rows x 128 pixels x all (<= 128) output channels:
-//     two 128 x N fp32 accumulators in TMEM (2N <= 256 columns, so two CTAs share an SM: one CTA's epilogue and prologue
-//     run under the other's MMAs).
-//   * K is walked as (16-channel chunk) x (tap).  Per chunk the producers (6 warps) convert the input rows the nine taps
-//     touch -- (R + 2d) rows (or 3R for large dilations) x (128 + 2d) pixels -- from fp32 NCHW into split bf16 in the
-//     *no-swizzle K-major core-matrix layout*: plane [8-channel group][pixel] with 16 bytes per entry.  In that layout a
-//     tap shift is nothing but a different start address (+16 bytes per pixel), so all nine taps are nine shared-memory
-//     descriptors over ONE converted tile: (start, LBO = plane pitch, SBO = 128 B).
+//   * M tile = 128 consecutive output pixels of one image row; a work tile is R = 2 rows x 128 pixels x all output channels
+//     (two 128 x N fp32 accumulators in TMEM).  PERSISTENT kernel, one CTA per SM, tiles dealt round-robin; the
+//     accumulators are double-buffered in TMEM (2 x 2N <= 512 columns for N <= 128), so tile i's epilogue runs under tile
+//     i+1's MMAs, and the producers / weight loader simply run ahead across tile boundaries.
+//   * K is walked as (16-channel chunk) x (tap).  Per chunk the producer warps convert the input rows the nine taps touch
+//     from fp32 NCHW into split bf16 in the *no-swizzle K-major core-matrix layout*: plane [8-channel group][pixel] with
+//     16 bytes per entry.  In that layout a tap shift is nothing but a different start address (+16 bytes per pixel), so
+//     all nine taps are nine shared-memory descriptors over ONE converted tile: (start, LBO = plane pitch, SBO = 128 B).
+//     Stride 2 de-interleaves even / odd pixels so the same holds (see the geometry helpers).
 //   * weights are pre-packed (mfn_conv3x3_pack_weights) into per-(chunk, tap) images of the same layout and streamed by
-//     one thread with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) through a 4-stage ring.
+//     one thread with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) through a deep ring (up to 16 stages: the
+//     L2 -> shared latency of a tile is several times its MMA time).
 //   * one thread issues the MMAs (M=128, N=CoutP, K=16, kind::f16, bf16 x bf16 -> fp32); tcgen05.commit releases the
-//     weight / input stages and finally signals the epilogue warps, which read the accumulators with tcgen05.ld
-//     (lane = pixel, 32 output channels per instruction), add the bias, apply LeakyReLU and store NCHW (coalesced 128 B
-//     per plane row and warp).
+//     weight / input stages and signals the four epilogue warps, which read the accumulators with tcgen05.ld (lane =
+//     pixel, 16 output channels per instruction), add the bias, apply LeakyReLU and store NCHW (coalesced 128 B per
+//     plane row and warp) -- or, for the transposed convolutions, scatter 2x2 sub-pixel phases (depth-to-space).
 #include "mma_tiles.cuh"
 
 namespace mfn {
@@ -27,10 +29,11 @@ using c3::split_pair;
 
 constexpr int MT = 128;          // pixels per M tile
 constexpr int R = 2;             // output rows per CTA
-constexpr int NTHREADS = 256;
-constexpr int NPROD = 6;         // producer warps (warps 2..7); warps 4..7 double as epilogue warps
-constexpr int WSTAGES = 4;
+constexpr int NTHREADS = 512;    // warp 0: MMA issuer + TMEM owner, warp 1: weight loader, warps 4..7: epilogue, rest: producers
+constexpr int NPROD = 10;        // producer warps: 2, 3, 8..15
+constexpr int MAX_AS = 4, MAX_WS = 16;
 constexpr int BATCH = 4;         // producer items (32 entries x 8 channels) in flight per warp
+constexpr int BAR_BYTES = 512;   // a_full/a_empty [MAX_AS], w_full/w_empty [MAX_WS], acc_full/acc_empty [2], TMEM pointer
 
 // Geometry of the converted input tile: `nslots` image rows of PW entries each.
 //   stride 1 (any dilation d): rows y0 - d .. y0 + R - 1 + d (or the 3R rows the taps touch when d >= R); entry p of a row is
@@ -106,16 +109,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 struct SmemMap {
-  int a_lo, a_stage, w_tile, w_off, bar_off, total;
+  int a_lo, a_stage, w_tile, w_off, bar_off, total, AS, WS;
 };
+// stage counts from the shared-memory budget: 3 input stages when that still leaves >= 8 weight stages, else 2
 __host__ __device__ inline SmemMap smem_map(int E, int CoutP) {
   SmemMap m;
   m.a_lo = 2 * E * 16;              // hi image: two 8-channel planes of E entries
   m.a_stage = 2 * m.a_lo;           // hi + lo
   m.w_tile = 64 * CoutP;            // [hi | lo][2 planes][CoutP][16 B]
-  m.w_off = 2 * m.a_stage;
-  m.bar_off = m.w_off + WSTAGES * m.w_tile;
-  m.total = m.bar_off + 16 * 8;
+  const int budget = 227 * 1024 - BAR_BYTES;
+  m.AS = (3 * m.a_stage + 8 * m.w_tile <= budget) ? 3 : 2;
+  int ws = (budget - m.AS * m.a_stage) / m.w_tile;
+  m.WS = ws > MAX_WS ? MAX_WS : ws;
+  m.w_off = m.AS * m.a_stage;
+  m.bar_off = m.w_off + m.WS * m.w_tile;
+  m.total = m.bar_off + BAR_BYTES;
   return m;
 }
 }  // namespace um
@@ -145,44 +153,43 @@ __global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned c
   }
 }
 
-__global__ void __launch_bounds__(um::NTHREADS, 2)
+__global__ void __launch_bounds__(um::NTHREADS, 1)
     conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
                         const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
-                        int OH, int OW, int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int stride,
-                        int dil, int tmem_cols) {
+                        int OH, int OW, int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int numTiles,
+                        int stride, int dil, int out_mode, int tmem_cols, int nacc) {
   using namespace um;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nslots = n_slots(stride, dil), PW = row_pitch(stride, dil), E = nslots * PW;
   const SmemMap sm = smem_map(E, CoutP);
+  const int AS = sm.AS, WS = sm.WS;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + sm.bar_off;
-  // barriers: a_full[2] @0,8  a_empty[2] @16,24  w_full[4] @32..  w_empty[4] @64..  acc_full @96;  tmem pointer @104
-  const uint32_t a_full = bar0, a_empty = bar0 + 16, w_full = bar0 + 32, w_empty = bar0 + 64, acc_full = bar0 + 96;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + sm.bar_off + 104);
+  const uint32_t a_full = bar0, a_empty = bar0 + 8 * MAX_AS, w_full = bar0 + 16 * MAX_AS, w_empty = w_full + 8 * MAX_WS,
+                 acc_full = w_empty + 8 * MAX_WS, acc_empty = acc_full + 16, tmem_ptr = acc_empty + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + sm.bar_off + (tmem_ptr - bar0));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
-  const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
-  const int x0 = tx * MT, y0 = ty * R;
-  const size_t plane = (size_t)H * W, oplane = (size_t)OH * OW;
+  const size_t plane = (size_t)H * W;
   const int nIter = nChunks * 9;
 
   if (tid == 0) {
-    mbar_init(a_full, NPROD);
-    mbar_init(a_full + 8, NPROD);
-    mbar_init(a_empty, 1);
-    mbar_init(a_empty + 8, 1);
-    for (int i = 0; i < WSTAGES; ++i) {
+    for (int i = 0; i < AS; ++i) {
+      mbar_init(a_full + 8 * i, NPROD);
+      mbar_init(a_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < WS; ++i) {
       mbar_init(w_full + 8 * i, 1);
       mbar_init(w_empty + 8 * i, 1);
     }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + 8 * i, 1);
+      mbar_init(acc_empty + 8 * i, 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {   // TMEM allocation: one warp, address lands in shared memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + sm.bar_off + 104),
-                 "r"(tmem_cols)
-                 : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -196,113 +203,155 @@ __global__ void __launch_bounds__(um::NTHREADS, 2)
       // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), K-major both, N >> 3 @17, M >> 4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CoutP >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
       const uint32_t a_lbo = (uint32_t)E * 16u, b_lbo = (uint32_t)CoutP * 16u;
-      for (int c = 0; c < nChunks; ++c) {
-        mbar_wait(a_full + 8 * (c & 1), (uint32_t)((c >> 1) & 1));
+      uint32_t a_cnt = 0, w_cnt = 0, j = 0;
+      for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
+        const uint32_t acc = j % (uint32_t)nacc;
+        if (j >= (uint32_t)nacc) mbar_wait(acc_empty + 8 * acc, ((j / (uint32_t)nacc) + 1) & 1);   // epilogue drained it
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_st = s_base + (uint32_t)((c & 1) * sm.a_stage);
-        for (int tap = 0; tap < 9; ++tap) {
-          const int it = c * 9 + tap, ws = it % WSTAGES;
-          const int ky = tap / 3, kx = tap - 3 * ky;
-          mbar_wait(w_full + 8 * ws, (uint32_t)((it / WSTAGES) & 1));
+        const uint32_t d0 = tmem_base + acc * (uint32_t)(R * CoutP);
+        for (int c = 0; c < nChunks; ++c, ++a_cnt) {
+          const uint32_t as = a_cnt % (uint32_t)AS;
+          mbar_wait(a_full + 8 * as, (a_cnt / (uint32_t)AS) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t w_st = s_base + (uint32_t)(sm.w_off + ws * sm.w_tile);
-          const uint64_t b_hi = smem_desc(w_st, b_lbo, 128), b_lo = smem_desc(w_st + (uint32_t)(sm.w_tile / 2), b_lbo, 128);
+          const uint32_t a_st = s_base + as * (uint32_t)sm.a_stage;
+          for (int tap = 0; tap < 9; ++tap, ++w_cnt) {
+            const uint32_t ws = w_cnt % (uint32_t)WS;
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            mbar_wait(w_full + 8 * ws, (w_cnt / (uint32_t)WS) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t w_st = s_base + (uint32_t)sm.w_off + ws * (uint32_t)sm.w_tile;
+            const uint64_t b_hi = smem_desc(w_st, b_lbo, 128), b_lo = smem_desc(w_st + (uint32_t)(sm.w_tile / 2), b_lbo, 128);
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const uint32_t a_addr = a_st + (uint32_t)((slot_of(r, ky, stride, dil) * PW + tap_xoff(kx, stride, dil)) * 16);
-            const uint64_t a_hi = smem_desc(a_addr, a_lbo, 128), a_lo = smem_desc(a_addr + (uint32_t)sm.a_lo, a_lbo, 128);
-            const uint32_t d = tmem_base + (uint32_t)(r * CoutP);
-            umma_bf16(d, a_hi, b_lo, idesc, it > 0 ? 1u : 0u);
-            umma_bf16(d, a_lo, b_hi, idesc, 1u);
-            umma_bf16(d, a_hi, b_hi, idesc, 1u);
+            for (int r = 0; r < R; ++r) {
+              const uint32_t a_addr = a_st + (uint32_t)((slot_of(r, ky, stride, dil) * PW + tap_xoff(kx, stride, dil)) * 16);
+              const uint64_t a_hi = smem_desc(a_addr, a_lbo, 128), a_lo = smem_desc(a_addr + (uint32_t)sm.a_lo, a_lbo, 128);
+              const uint32_t d = d0 + (uint32_t)(r * CoutP);
+              umma_bf16(d, a_hi, b_lo, idesc, (c | tap) ? 1u : 0u);
+              umma_bf16(d, a_lo, b_hi, idesc, 1u);
+              umma_bf16(d, a_hi, b_hi, idesc, 1u);
+            }
+            umma_commit(w_empty + 8 * ws);       // weight stage free once these MMAs have read it
           }
-          umma_commit(w_empty + 8 * ws);       // weight stage free once these MMAs have read it
+          umma_commit(a_empty + 8 * as);         // input stage free
         }
-        umma_commit(a_empty + 8 * (c & 1));    // input stage free
+        umma_commit(acc_full + 8 * acc);         // this tile's accumulators are complete
       }
-      umma_commit(acc_full);                   // accumulators complete
     }
   } else if (warp == 1) {
     // ============================ weight loader (one thread) ============================
     if (lane == 0) {
-      for (int it = 0; it < nIter; ++it) {
-        const int ws = it % WSTAGES;
-        if (it >= WSTAGES) mbar_wait(w_empty + 8 * ws, (uint32_t)(((it / WSTAGES) + 1) & 1));
-        mbar_arrive_expect_tx(w_full + 8 * ws, (uint32_t)sm.w_tile);
-        bulk_g2s(s_base + (uint32_t)(sm.w_off + ws * sm.w_tile), wpack + (size_t)it * sm.w_tile, (uint32_t)sm.w_tile,
-                 w_full + 8 * ws);
-      }
-    }
-  } else {
-    // ============================ input producers (warps 2..7) ============================
-    const int pw = warp - 2;
-    const float* xn = x + (size_t)n * x_bs;
-    const int G = (E + 31) / 32, nItems = 2 * G;       // item = (32 entries, 8-channel plane)
-    for (int c = 0; c < nChunks; ++c) {
-      if (c >= 2) mbar_wait(a_empty + 8 * (c & 1), (uint32_t)(((c >> 1) + 1) & 1));
-      unsigned char* a_st = smem + (c & 1) * sm.a_stage;
-      for (int k0 = pw; k0 < nItems; k0 += NPROD * BATCH) {
-        float v[BATCH][8];
-#pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-          const int t = k0 + b * NPROD;
-          const int kc = t & 1, e = (t >> 1) * 32 + lane;
-          const int slot = e / PW, p = e - slot * PW;
-          const int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(p, x0, stride, dil);
-          const bool ok = t < nItems && e < E && y >= 0 && y < H && xx >= 0 && xx < W;
-          const int c0 = 16 * c + 8 * kc;
-          const float* src = xn + (size_t)c0 * plane + (size_t)(ok ? y : 0) * W + (ok ? xx : 0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[b][j] = (ok && c0 + j < Cin) ? __ldg(src) : 0.f;
-            src += plane;
-          }
-        }
-#pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-          const int t = k0 + b * NPROD;
-          const int kc = t & 1, e = (t >> 1) * 32 + lane;
-          if (t < nItems && e < E) {
-            uint4 hi, lo;
-            split_pair(v[b][0], v[b][1], hi.x, lo.x);
-            split_pair(v[b][2], v[b][3], hi.y, lo.y);
-            split_pair(v[b][4], v[b][5], hi.z, lo.z);
-            split_pair(v[b][6], v[b][7], hi.w, lo.w);
-            unsigned char* dst = a_st + (kc * E + e) * 16;
-            *reinterpret_cast<uint4*>(dst) = hi;
-            *reinterpret_cast<uint4*>(dst + sm.a_lo) = lo;
-          }
+      uint32_t w_cnt = 0;
+      for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        for (int it = 0; it < nIter; ++it, ++w_cnt) {
+          const uint32_t ws = w_cnt % (uint32_t)WS;
+          if (w_cnt >= (uint32_t)WS) mbar_wait(w_empty + 8 * ws, ((w_cnt / (uint32_t)WS) + 1) & 1);
+          mbar_arrive_expect_tx(w_full + 8 * ws, (uint32_t)sm.w_tile);
+          bulk_g2s(s_base + (uint32_t)sm.w_off + ws * (uint32_t)sm.w_tile, wpack + (size_t)it * sm.w_tile,
+                   (uint32_t)sm.w_tile, w_full + 8 * ws);
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + 8 * (c & 1));
     }
-    // ============================ epilogue (warps 4..7: TMEM lanes 32*(warp&3) ..) ============================
-    if (warp >= 4) {
-      mbar_wait(acc_full, 0);
+  } else if (warp >= 4 && warp < 8) {
+    // ============================ epilogue (TMEM lanes 32*(warp&3) .. +31 = pixels of the M tile) ============================
+    const int q = warp & 3;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
+      const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+      const uint32_t acc = j % (uint32_t)nacc;
+      mbar_wait(acc_full + 8 * acc, (j / (uint32_t)nacc) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int q = warp & 3;
-      const int xx = x0 + 32 * q + lane;
+      const int xx = tx * MT + 32 * q + lane;
 #pragma unroll 1
       for (int r = 0; r < R; ++r) {
-        const int y = y0 + r;
-        float* on = out + (size_t)n * out_bs + (size_t)y * OW + xx;
+        const int y = ty * R + r;
         const bool okp = y < OH && xx < OW;
+        const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + acc * (uint32_t)(R * CoutP) + (uint32_t)(r * CoutP);
 #pragma unroll 1
         for (int nc = 0; nc < CoutP / 16; ++nc) {
           uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(r * CoutP + nc * 16), v);
+          tmem_ld16(t0 + (uint32_t)(nc * 16), v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (out_mode == 0) {
+            float* on = out + (size_t)n * out_bs + (size_t)y * OW + xx;
+            const size_t oplane = (size_t)OH * OW;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int f = nc * 16 + j;
-            if (f < Cout && okp) {
-              const float b = bias ? __ldg(bias + f) : 0.f;
-              on[(size_t)f * oplane] = leaky(__uint_as_float(v[j]) + b, slope);
+            for (int jj = 0; jj < 16; ++jj) {
+              const int f = nc * 16 + jj;
+              if (f < Cout && okp) {
+                const float b = bias ? __ldg(bias + f) : 0.f;
+                on[(size_t)f * oplane] = leaky(__uint_as_float(v[jj]) + b, slope);
+              }
+            }
+          } else {
+            // depth-to-space: conv channel f' = (2 py + px) * F + f  ->  out[n][f][2y + py][2x + px], out is (F, 2 OH, 2 OW)
+            const int F = Cout >> 2;
+            const size_t oplane = (size_t)(2 * OH) * (2 * OW);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int fp = nc * 16 + jj;
+              if (fp < Cout && okp) {
+                const int ph = fp / F, f = fp - ph * F;
+                const float b = bias ? __ldg(bias + f) : 0.f;
+                out[(size_t)n * out_bs + (size_t)f * oplane + (size_t)(2 * y + (ph >> 1)) * (2 * OW) + 2 * xx + (ph & 1)] =
+                    leaky(__uint_as_float(v[jj]) + b, slope);
+              }
             }
           }
         }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * acc);   // TMEM reads of this accumulator are done (wait::ld above)
+    }
+  } else {
+    // ============================ input producers (warps 2, 3, 8..15) ============================
+    const int pw = warp < 4 ? warp - 2 : warp - 6;
+    const int G = (E + 31) / 32, nItems = 2 * G;       // item = (32 entries, 8-channel plane)
+    uint32_t a_cnt = 0;
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+      const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+      const int x0 = tx * MT, y0 = ty * R;
+      const float* xn = x + (size_t)n * x_bs;
+      for (int c = 0; c < nChunks; ++c, ++a_cnt) {
+        const uint32_t as = a_cnt % (uint32_t)AS;
+        if (a_cnt >= (uint32_t)AS) mbar_wait(a_empty + 8 * as, ((a_cnt / (uint32_t)AS) + 1) & 1);
+        unsigned char* a_st = smem + as * sm.a_stage;
+        for (int k0 = pw; k0 < nItems; k0 += NPROD * BATCH) {
+          float v[BATCH][8];
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) {
+            const int t = k0 + b * NPROD;
+            const int kc = t & 1, e = (t >> 1) * 32 + lane;
+            const int slot = e / PW, p = e - slot * PW;
+            const int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(p, x0, stride, dil);
+            const bool ok = t < nItems && e < E && y >= 0 && y < H && xx >= 0 && xx < W;
+            const int c0 = 16 * c + 8 * kc;
+            const float* src = xn + (size_t)c0 * plane + (size_t)(ok ? y : 0) * W + (ok ? xx : 0);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              v[b][jj] = (ok && c0 + jj < Cin) ? __ldg(src) : 0.f;
+              src += plane;
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) {
+            const int t = k0 + b * NPROD;
+            const int kc = t & 1, e = (t >> 1) * 32 + lane;
+            if (t < nItems && e < E) {
+              uint4 hi, lo;
+              split_pair(v[b][0], v[b][1], hi.x, lo.x);
+              split_pair(v[b][2], v[b][3], hi.y, lo.y);
+              split_pair(v[b][4], v[b][5], hi.z, lo.z);
+              split_pair(v[b][6], v[b][7], hi.w, lo.w);
+              unsigned char* dst = a_st + (kc * E + e) * 16;
+              *reinterpret_cast<uint4*>(dst) = hi;
+              *reinterpret_cast<uint4*>(dst + sm.a_lo) = lo;
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + 8 * as);
       }
     }
   }
@@ -329,14 +378,14 @@ int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int C
 
 // returns -1 when the shape does not fit this kernel (caller falls back to the mma.sync kernel)
 int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
-                        long long out_bs, int N, int Cin, int H, int W, int Cout, int stride, int dil, float slope,
-                        cudaStream_t st) {
+                        long long out_bs, int N, int Cin, int H, int W, int Cout, int stride, int dil, int out_mode,
+                        float slope, cudaStream_t st) {
   using namespace um;
   if (Cout > 256 || (stride != 1 && !(stride == 2 && dil == 1))) return -1;
   const int CoutP = um::cout_pad(Cout), nChunks = (Cin + 15) / 16;
   const int E = n_slots(stride, dil) * row_pitch(stride, dil);
   const SmemMap sm = smem_map(E, CoutP);
-  if (sm.total > 227 * 1024 || E * 16 > 0x3FFF * 16) return -1;
+  if (sm.WS < 2 || E * 16 > 0x3FFF * 16) return -1;
   const int OH = stride == 2 ? (H - 1) / 2 + 1 : H, OW = stride == 2 ? (W - 1) / 2 + 1 : W;
   static int configured = 0;
   if (configured < sm.total) {
@@ -344,12 +393,16 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(conv3x3_umma_kernel): %s", cudaGetErrorString(e));
     configured = sm.total;
   }
+  const int nacc = 2 * R * CoutP <= 512 ? 2 : 1;   // double-buffered accumulators when they fit the 512 TMEM columns
   int cols = 32;
-  while (cols < R * CoutP) cols *= 2;
+  while (cols < nacc * R * CoutP) cols *= 2;
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
-  const unsigned grid = (unsigned)((long long)N * tilesX * tilesY);
+  const long long numTiles = (long long)N * tilesX * tilesY;
+  const int cap = tuning().conv_grid_cap > 0 ? tuning().conv_grid_cap : kNumSMs;
+  const unsigned grid = (unsigned)(numTiles < cap ? numTiles : cap);
   conv3x3_umma_kernel<<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout, CoutP,
-                                                        nChunks, slope, tilesX, tilesY, stride, dil, cols);
+                                                        nChunks, slope, tilesX, tilesY, (int)numTiles, stride, dil, out_mode,
+                                                        cols, nacc);
   return check_launch("conv3x3_umma_kernel");
 }
 

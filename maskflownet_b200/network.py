@@ -78,6 +78,54 @@ class _FlowNetBase(nn.Module):
             cache[name] = (key, ops.conv3x3_pack(w))
         return cache[name][1]
 
+    def _packed_fn(self, key, params, build):
+        """Cached derived tensors (fused / re-arranged weight images), rebuilt when any source parameter changes."""
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        ver = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        hit = cache.get(key)
+        if hit is None or hit[0] != ver:
+            cache[key] = (ver, build())
+        return cache[key][1]
+
+    def _heads(self, lvl, x, with_mask):
+        """pred_flow{lvl} (2 channels) and pred_mask{lvl} (1 channel) read the same block output
+        (network/MaskFlownet.py:224, 226 ...): inference runs them as ONE 3-output convolution, no activation."""
+        pf = getattr(self, f"pred_flow{lvl}")
+        pm = getattr(self, f"pred_mask{lvl}") if with_mask else None
+        if not self._fast(x):
+            return pf(x), (pm(x) if pm is not None else None)
+        convs = [pf] + ([pm] if pm is not None else [])
+
+        def build():
+            w = torch.cat([c.weight.detach() for c in convs], dim=0).contiguous()
+            b = torch.cat([c.bias.detach() for c in convs], dim=0).contiguous()
+            return ops.conv3x3_pack(w), b
+        packed, b = self._packed_fn(f"heads{lvl}", [p for c in convs for p in (c.weight, c.bias)], build)
+        y = ops.conv3x3(x, packed, b, 2 + (1 if pm is not None else 0), 1.0)
+        if pm is None:
+            return y, None
+        return y[:, :2].contiguous(), y[:, 2:3].contiguous()
+
+    def _upfeat(self, lvl, x):
+        """feat = LeakyReLU(upfeat{lvl}(x)): ConvTranspose2d(4, 2, 1) as a 3x3 convolution + depth-to-space on the
+        tensor-core kernel (ops.conv_transpose4x4_pack)."""
+        up = getattr(self, f"upfeat{lvl}")
+        if not self._fast(x):
+            return tF.leaky_relu(up(x), SLOPE)
+        packed = self._packed_fn(f"upfeat{lvl}", [up.weight], lambda: ops.conv_transpose4x4_pack(up.weight))
+        N, C, H, W = x.shape
+        F = up.out_channels
+        out = torch.empty((N, F, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
+        ops.conv3x3_slices(x, 0, C, packed, up.bias, out, 0, 4 * F, SLOPE, depth_to_space=True)
+        return out
+
+    def _plain(self, name, x):
+        """3x3 convolution without activation (conv{L}f, dc_conv7)."""
+        conv = getattr(self, name)
+        if not self._fast(x):
+            return conv(x)
+        return ops.conv3x3(x, self._packed(name), conv.bias, conv.out_channels, 1.0, conv.dilation[0])
+
     def _fast(self, x):
         return self.use_tc_conv and x.is_cuda and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
 
@@ -135,7 +183,7 @@ class _FlowNetBase(nn.Module):
                 x = ops.conv3x3(x, self._packed(f"dc_conv{i}"), conv.bias, conv.out_channels, SLOPE, conv.dilation[0])
             else:
                 x = tF.leaky_relu(conv(x), SLOPE)
-        return self.dc_conv7(x)
+        return self._plain("dc_conv7", x)
 
     def _make_decoder(self, in_ch: Dict[int, int], with_mask: bool, upfeat_ch):
         for lvl in (6, 5, 4, 3, 2):
@@ -216,13 +264,12 @@ class MaskFlownetS(_FlowNetBase):
         (network/MaskFlownet.py:302-315).  srcs (needed only by the cascade) is built when want_cascade_inputs."""
         c1, c2 = self._pyramid_pair(im1, im2, "abc")
         x = self._corr_block(6, c1[5], c2[5], [])   # correlation + dense block
-        flow = self.pred_flow6(x)
-        mask = self.pred_mask6(x)
+        flow, mask = self._heads(6, x, True)
         flows = [flow]
         for lvl in (5, 4, 3, 2):
-            feat = tF.leaky_relu(getattr(self, f"upfeat{lvl}")(x), SLOPE)
+            feat = self._upfeat(lvl, x)
             dp = getattr(self, f"deform{lvl}")
-            trade = getattr(self, f"conv{lvl}f")(feat)
+            trade = self._plain(f"conv{lvl}f", feat)
             if self.event_hook is not None:
                 self.event_hook("warp", lvl, 0)
             warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, mask, dp.weight, dp.bias, trade, self.scale,
@@ -233,9 +280,10 @@ class MaskFlownetS(_FlowNetBase):
             if self.event_hook is not None:
                 self.event_hook("warp", lvl, 1)
             x = self._corr_block(lvl, c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up])
-            flow = flow_up + getattr(self, f"pred_flow{lvl}")(x)
+            dflow, m = self._heads(lvl, x, lvl > 2)
+            flow = flow_up + dflow
             if lvl > 2:
-                mask = getattr(self, f"pred_mask{lvl}")(x)
+                mask = m
             else:
                 mask_up2 = _  # Upsample(2)(mask3): the level-2 occlusion mask (network/MaskFlownet.py:283)
             flows.append(flow)
@@ -291,16 +339,16 @@ class MaskFlownet(_FlowNetBase):
         warp, _, _ = ops.warp_mask(c2[5], flow, None, dp.weight, dp.bias, None, self.scale, float(STRIDES[6]), 1,
                                    SLOPE, self.border_mode)
         x = self._dense(6, torch.cat([self._corr(c1[5], warp), self._corr(c3[5], c4[5]), flow], dim=1))
-        flow = flow + self.pred_flow6(x)
+        flow = flow + self._heads(6, x, False)[0]
         flows = [flow]
         for i, lvl in enumerate((5, 4, 3, 2)):
-            feat = tF.leaky_relu(getattr(self, f"upfeat{lvl}")(x), SLOPE)
+            feat = self._upfeat(lvl, x)
             dp = getattr(self, f"deform{lvl}")
             warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, None, dp.weight, dp.bias, None, self.scale,
                                              float(STRIDES[lvl]), 2, SLOPE, self.border_mode)
             x = self._dense(lvl, torch.cat([c1[lvl - 1], feat, self._corr(c1[lvl - 1], warp),
                                             self._corr(c3[lvl - 1], c4[lvl - 1]), flow_up, flows_s[i + 1]], dim=1))
-            flow = flow_up + getattr(self, f"pred_flow{lvl}")(x)
+            flow = flow_up + self._heads(lvl, x, False)[0]
             flows.append(flow)
         flows[-1] = flow = flow + self._context(x)
         return [f * self.scale for f in flows], [flow[:, 0:1]], []

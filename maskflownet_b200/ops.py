@@ -375,27 +375,51 @@ def conv3x3_pack(weight: torch.Tensor) -> torch.Tensor:
 
 def conv3x3_slices(buf_in: torch.Tensor, c_in0: int, Cin: int, packed: torch.Tensor, bias: Optional[torch.Tensor],
                    buf_out: torch.Tensor, c_out0: int, Cout: int, leaky_slope: float = 0.1, dilation: int = 1,
-                   stride: int = 1) -> None:
+                   stride: int = 1, depth_to_space: bool = False) -> None:
     """out = LeakyReLU(conv3x3(buf_in[:, c_in0:c_in0+Cin]) + bias) written to buf_out[:, c_out0:c_out0+Cout]; both buffers
     dense NCHW (they may be the same tensor: the dense block's concat buffer).  stride 2 (pad 1) = the pyramid's
-    down-sampling convolutions: buf_out is then ((H-1)//2+1, (W-1)//2+1).  Inference only (no autograd)."""
+    down-sampling convolutions: buf_out is then ((H-1)//2+1, (W-1)//2+1).  depth_to_space: the Cout = 4F conv channels
+    are written as F channels of a (2H, 2W) image (sub-pixel phases; see conv_transpose4x4_pack).  Inference only."""
     for t, nm in ((buf_in, "buf_in"), (buf_out, "buf_out")):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4):
             raise MaskflowError(f"conv3x3_slices: {nm} must be a contiguous CUDA float32 NCHW tensor")
     N, Cti, H, W = buf_in.shape
     OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if depth_to_space:
+        OH, OW = 2 * OH, 2 * OW
+    Fo = Cout // 4 if depth_to_space else Cout        # channels written
     if buf_out.shape[0] != N or tuple(buf_out.shape[2:]) != (OH, OW):
         raise MaskflowError("conv3x3_slices: buffers disagree in N/H/W")
     Cto = buf_out.shape[1]
-    if not (0 <= c_in0 and c_in0 + Cin <= Cti and 0 <= c_out0 and c_out0 + Cout <= Cto):
+    if not (0 <= c_in0 and c_in0 + Cin <= Cti and 0 <= c_out0 and c_out0 + Fo <= Cto):
         raise MaskflowError("conv3x3_slices: channel slice out of range")
     if buf_in.data_ptr() == buf_out.data_ptr() and not (c_out0 + Cout <= c_in0 or c_in0 + Cin <= c_out0):
         raise MaskflowError("conv3x3_slices: input and output slices overlap")
     b = _chk(bias, "conv3x3_slices.bias", optional=True)
     xin = ctypes.c_void_p(buf_in.data_ptr() + 4 * c_in0 * H * W)
     xout = ctypes.c_void_p(buf_out.data_ptr() + 4 * c_out0 * OH * OW)
-    _call("mfn_conv3x3_forward_strided", buf_in.device, xin, Cti * H * W, _p(packed), _p(b), xout, Cto * OH * OW, N, Cin, H, W,
-          Cout, int(stride), int(dilation), float(leaky_slope))
+    _call("mfn_conv3x3_forward_ex", buf_in.device, xin, Cti * H * W, _p(packed), _p(b), xout, Cto * OH * OW, N, Cin, H, W,
+          Cout, int(stride), int(dilation), 1 if depth_to_space else 0, float(leaky_slope))
+
+
+def conv_transpose4x4_pack(weight: torch.Tensor) -> torch.Tensor:
+    """nn.ConvTranspose2d(Cin, F, kernel 4, stride 2, pad 1) (the decoder's `upfeat` layers, network/MaskFlownet.py:225 ...)
+    as a 3x3 convolution with 4F outputs + depth-to-space: output pixel (2y+py, 2x+px) only touches inputs (y+dy, x+dx)
+    with dy in {0, -1} (py = 0) or {0, +1} (py = 1), kernel row ky = py + 1 - 2 dy.  Returns the packed 3x3 weights
+    (conv channel (2 py + px) * F + f); the five unused taps of every phase are zero."""
+    w = _chk(weight.detach(), "conv_transpose4x4_pack.weight")       # (Cin, F, 4, 4)
+    Cin, F, kh, kw = w.shape
+    if (kh, kw) != (4, 4):
+        raise MaskflowError("conv_transpose4x4_pack: weight must be (Cin, F, 4, 4)")
+    w3 = torch.zeros((4 * F, Cin, 3, 3), device=w.device, dtype=torch.float32)
+    for py in range(2):
+        for px in range(2):
+            ph = 2 * py + px
+            for dy in ((0, -1) if py == 0 else (0, 1)):
+                for dx in ((0, -1) if px == 0 else (0, 1)):
+                    ky, kx = py + 1 - 2 * dy, px + 1 - 2 * dx
+                    w3[ph * F:(ph + 1) * F, :, dy + 1, dx + 1] = w[:, :, ky, kx].t()
+    return conv3x3_pack(w3)
 
 
 def conv3x3(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], Cout: int, leaky_slope: float = 0.1,

@@ -428,6 +428,44 @@ def test_conv3x3_stride2_pyramid(N, Cin, Cout, H, W):
     assert np.abs(got1 - ref1).max() <= 1e-4 * max(1.0, float(np.abs(ref1).max())), _lib.last_kernel()
 
 
+@pytest.mark.parametrize("N,Cin,F,H,W", [(1, 20, 16, 7, 16), (2, 70, 16, 9, 130), (1, 33, 8, 5, 40)])
+def test_conv_transpose4x4_as_conv3x3_depth_to_space(N, Cin, F, H, W):
+    """upfeat{L}: nn.Conv2DTranspose(kernel 4, stride 2, pad 1) + LeakyReLU (network/MaskFlownet.py:225 ...) through the
+    3x3 kernel with the depth-to-space epilogue."""
+    rng = np.random.default_rng(47)
+    x = feat(rng, (N, Cin, H, W))
+    w = (rng.standard_normal((Cin, F, 4, 4)) * np.sqrt(2.0 / (4 * Cin))).astype(np.float32)
+    b = (rng.standard_normal(F) * 0.1).astype(np.float32)
+    ref = torch.nn.functional.conv_transpose2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(),
+                                               torch.from_numpy(b).double(), stride=2, padding=1)
+    ref = torch.nn.functional.leaky_relu(ref, 0.1).float().numpy()
+    packed = ops.conv_transpose4x4_pack(cu(w))
+    out = torch.full((N, F + 3, 2 * H, 2 * W), float("nan"), device=DEV)
+    ops.conv3x3_slices(cu(x), 0, Cin, packed, cu(b), out, 2, 4 * F, 0.1, depth_to_space=True)
+    got = out[:, 2:2 + F].cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max()))
+    assert torch.isnan(out[:, :2]).all() and torch.isnan(out[:, 2 + F:]).all()      # neighbouring slices untouched
+
+
+@pytest.mark.parametrize("cap", [1, 3])
+def test_conv3x3_persistent_tile_loop(cap):
+    """The tcgen05 kernel is persistent: with the grid capped every CTA walks many tiles (stage rings wrap, barrier
+    parities flip, TMEM accumulators alternate); results must not depend on the grid size."""
+    rng = np.random.default_rng(49)
+    N, Cin, Cout, H, W = 2, 50, 64, 13, 150
+    x = feat(rng, (N, Cin, H, W))
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(
+        torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=1), 0.1).float().numpy()
+    _lib.set_tuning("conv_grid_cap", cap)
+    try:
+        got = ops.conv3x3(cu(x), ops.conv3x3_pack(cu(w)), cu(b), Cout, 0.1).cpu().numpy()
+    finally:
+        _lib.set_tuning("conv_grid_cap", 0)
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max()))
+
+
 def test_conv3x3_in_place_concat_block():
     """The dense block: five convolutions reading / writing channel slices of one buffer == torch.cat chain."""
     rng = np.random.default_rng(32)

@@ -25,7 +25,8 @@ for shp in [(1, 16, 32, 4, 128), (1, 16, 128, 2, 128), (1, 32, 64, 5, 130), (2, 
             (1, 579, 128, 10, 24), (1, 64, 96, 9, 256), (1, 40, 96, 21, 45, 2), (1, 40, 96, 21, 45, 4), (1, 40, 64, 21, 45, 16), (1, 128, 128, 30, 200, 8)]:
     check(*shp)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for (N, Cin, Cout, H, W, stride) in [(16, 3, 16, 448, 1024, 2), (16, 16, 16, 224, 512, 1), (16, 16, 32, 224, 512, 2), (16, 32, 32, 112, 256, 1),
+for (N, Cin, Cout, H, W, stride) in [(8, 131, 128, 112, 256, 1), (8, 565, 32, 112, 256, 1), (8, 259, 128, 56, 128, 1), (8, 341, 128, 28, 64, 1),
+                                     (16, 3, 16, 448, 1024, 2), (16, 16, 16, 224, 512, 1), (16, 16, 32, 224, 512, 2), (16, 32, 32, 112, 256, 1),
                                      (16, 32, 64, 112, 256, 2), (16, 64, 64, 56, 128, 1), (16, 64, 96, 56, 128, 2), (16, 96, 96, 28, 64, 1),
                                      (16, 96, 128, 28, 64, 2), (16, 128, 128, 14, 32, 1), (16, 128, 196, 14, 32, 2), (16, 196, 196, 7, 16, 1),
                                      (8, 597, 2, 112, 256, 1), (8, 16, 32, 112, 256, 1)]:
