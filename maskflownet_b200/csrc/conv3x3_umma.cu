@@ -203,51 +203,65 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), K-major both, N >> 3 @17, M >> 4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CoutP >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
       const uint32_t a_lbo = (uint32_t)E * 16u, b_lbo = (uint32_t)CoutP * 16u;
-      uint32_t a_cnt = 0, w_cnt = 0, j = 0;
+      // the issue loop is the one serial resource of the CTA: ring positions / parities are running counters (no
+      // divisions) and the 18 tap offsets live in registers (the tap loop is fully unrolled)
+      uint32_t a_off[9][R];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          a_off[tap][r] = (uint32_t)((slot_of(r, tap / 3, stride, dil) * PW + tap_xoff(tap % 3, stride, dil)) * 16);
+      const uint64_t desc_hi_a = ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+      const uint64_t desc_hi_b = ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+      auto adesc = [&](uint32_t addr) { return desc_hi_a | (uint64_t)((addr >> 4) & 0x3FFFu); };
+      auto bdesc = [&](uint32_t addr) { return desc_hi_b | (uint64_t)((addr >> 4) & 0x3FFFu); };
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, acc = 0, accph = 0, j = 0;
+      const uint32_t w_base = s_base + (uint32_t)sm.w_off, w_half = (uint32_t)(sm.w_tile / 2);
       for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
-        const uint32_t acc = j % (uint32_t)nacc;
-        if (j >= (uint32_t)nacc) mbar_wait(acc_empty + 8 * acc, ((j / (uint32_t)nacc) + 1) & 1);   // epilogue drained it
+        if (j >= (uint32_t)nacc) mbar_wait(acc_empty + 8 * acc, accph ^ 1);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d0 = tmem_base + acc * (uint32_t)(R * CoutP);
-        for (int c = 0; c < nChunks; ++c, ++a_cnt) {
-          const uint32_t as = a_cnt % (uint32_t)AS;
-          mbar_wait(a_full + 8 * as, (a_cnt / (uint32_t)AS) & 1);
+        for (int c = 0; c < nChunks; ++c) {
+          mbar_wait(a_full + 8 * as, aph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_st = s_base + as * (uint32_t)sm.a_stage;
-          for (int tap = 0; tap < 9; ++tap, ++w_cnt) {
-            const uint32_t ws = w_cnt % (uint32_t)WS;
-            const int ky = tap / 3, kx = tap - 3 * ky;
-            mbar_wait(w_full + 8 * ws, (w_cnt / (uint32_t)WS) & 1);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(w_full + 8 * ws, wph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t w_st = s_base + (uint32_t)sm.w_off + ws * (uint32_t)sm.w_tile;
-            const uint64_t b_hi = smem_desc(w_st, b_lbo, 128), b_lo = smem_desc(w_st + (uint32_t)(sm.w_tile / 2), b_lbo, 128);
+            const uint32_t w_st = w_base + ws * (uint32_t)sm.w_tile;
+            const uint64_t b_hi = bdesc(w_st), b_lo = bdesc(w_st + w_half);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              const uint32_t a_addr = a_st + (uint32_t)((slot_of(r, ky, stride, dil) * PW + tap_xoff(kx, stride, dil)) * 16);
-              const uint64_t a_hi = smem_desc(a_addr, a_lbo, 128), a_lo = smem_desc(a_addr + (uint32_t)sm.a_lo, a_lbo, 128);
+              const uint32_t a_addr = a_st + a_off[tap][r];
+              const uint64_t a_hi = adesc(a_addr), a_lo = adesc(a_addr + (uint32_t)sm.a_lo);
               const uint32_t d = d0 + (uint32_t)(r * CoutP);
-              umma_bf16(d, a_hi, b_lo, idesc, (c | tap) ? 1u : 0u);
+              umma_bf16(d, a_hi, b_lo, idesc, (tap == 0 && c == 0) ? 0u : 1u);
               umma_bf16(d, a_lo, b_hi, idesc, 1u);
               umma_bf16(d, a_hi, b_hi, idesc, 1u);
             }
             umma_commit(w_empty + 8 * ws);       // weight stage free once these MMAs have read it
+            if (++ws == (uint32_t)WS) { ws = 0; wph ^= 1; }
           }
           umma_commit(a_empty + 8 * as);         // input stage free
+          if (++as == (uint32_t)AS) { as = 0; aph ^= 1; }
         }
         umma_commit(acc_full + 8 * acc);         // this tile's accumulators are complete
+        if (++acc == (uint32_t)nacc) { acc = 0; accph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ============================ weight loader (one thread) ============================
     if (lane == 0) {
-      uint32_t w_cnt = 0;
+      uint32_t ws = 0, wph = 0;
+      bool wrapped = false;
       for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        for (int it = 0; it < nIter; ++it, ++w_cnt) {
-          const uint32_t ws = w_cnt % (uint32_t)WS;
-          if (w_cnt >= (uint32_t)WS) mbar_wait(w_empty + 8 * ws, ((w_cnt / (uint32_t)WS) + 1) & 1);
+        const unsigned char* src = wpack;
+        for (int it = 0; it < nIter; ++it, src += sm.w_tile) {
+          if (wrapped) mbar_wait(w_empty + 8 * ws, wph ^ 1);
           mbar_arrive_expect_tx(w_full + 8 * ws, (uint32_t)sm.w_tile);
-          bulk_g2s(s_base + (uint32_t)sm.w_off + ws * (uint32_t)sm.w_tile, wpack + (size_t)it * sm.w_tile,
-                   (uint32_t)sm.w_tile, w_full + 8 * ws);
+          bulk_g2s(s_base + (uint32_t)sm.w_off + ws * (uint32_t)sm.w_tile, src, (uint32_t)sm.w_tile, w_full + 8 * ws);
+          if (++ws == (uint32_t)WS) { ws = 0; wph ^= 1; wrapped = true; }
         }
       }
     }

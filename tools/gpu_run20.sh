@@ -1,0 +1,4 @@
+#!/bin/bash
+echo "== tests conv"; timeout 600 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "conv" 2>&1 | tail -3
+echo "== try"; SKIP_CHECK=1 timeout 300 python tools/try_umma.py 2>&1 | tail -21
+echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --cpu-sample-steps 0 2>&1 | tail -1 | cut -c1-220

@@ -21,12 +21,13 @@ def check(N, Cin, Cout, H, W, dil=1):
         torch.cuda.synchronize()
         res[mode] = (float(np.abs(got.cpu().numpy() - ref).max()), _lib.last_kernel())
     print(f"N={N} Cin={Cin} Cout={Cout} H={H} W={W} dil={dil}: umma err {res[1][0]:.2e} [{res[1][1]}]  sync err {res[0][0]:.2e} [{res[0][1]}]", flush=True)
-for shp in [(1, 16, 32, 4, 128), (1, 16, 128, 2, 128), (1, 32, 64, 5, 130), (2, 81, 128, 7, 16), (2, 131, 128, 12, 40), (1, 35, 32, 9, 33),
+for shp in [] if os.environ.get("SKIP_CHECK") else [(1, 16, 32, 4, 128), (1, 16, 128, 2, 128), (1, 32, 64, 5, 130), (2, 81, 128, 7, 16), (2, 131, 128, 12, 40), (1, 35, 32, 9, 33),
             (1, 579, 128, 10, 24), (1, 64, 96, 9, 256), (1, 40, 96, 21, 45, 2), (1, 40, 96, 21, 45, 4), (1, 40, 64, 21, 45, 16), (1, 128, 128, 30, 200, 8)]:
     check(*shp)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+_lib.set_tuning("conv_umma", 1); _lib.set_tuning("conv_umma_min_w", 1)
 for (N, Cin, Cout, H, W, stride) in [(8, 131, 128, 112, 256, 1), (8, 565, 32, 112, 256, 1), (8, 259, 128, 56, 128, 1), (8, 341, 128, 28, 64, 1),
-                                     (16, 3, 16, 448, 1024, 2), (16, 16, 16, 224, 512, 1), (16, 16, 32, 224, 512, 2), (16, 32, 32, 112, 256, 1),
+                                     (8, 128, 128, 112, 256, 1), (8, 597, 64, 56, 128, 1), (16, 3, 16, 448, 1024, 2), (16, 16, 16, 224, 512, 1), (16, 16, 32, 224, 512, 2), (16, 32, 32, 112, 256, 1),
                                      (16, 32, 64, 112, 256, 2), (16, 64, 64, 56, 128, 1), (16, 64, 96, 56, 128, 2), (16, 96, 96, 28, 64, 1),
                                      (16, 96, 128, 28, 64, 2), (16, 128, 128, 14, 32, 1), (16, 128, 196, 14, 32, 2), (16, 196, 196, 7, 16, 1),
                                      (8, 597, 2, 112, 256, 1), (8, 16, 32, 112, 256, 1)]:
