@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmaskflow_b200.so")
+SO_PATH = os.environ.get("MFN_LIB_PATH") or os.path.join(_HERE, "libmaskflow_b200.so")   # MFN_LIB_PATH: A/B experiments
 _lib = None
 
 _f = ctypes.c_void_p  # device pointers travel as integers

@@ -29,8 +29,9 @@ using c3::split_pair;
 
 constexpr int MT = 128;          // pixels per M tile
 constexpr int R = 2;             // output rows per CTA
-constexpr int NTHREADS = 512;    // warp 0: MMA issuer + TMEM owner, warp 1: weight loader, warps 4..7: epilogue, rest: producers
-constexpr int NPROD = 10;        // producer warps: 2, 3, 8..15
+constexpr int NTHREADS = 512;    // warps 0, 2: MMA issuers (warp 0 owns TMEM), warp 1: weight loader, warps 4..7: epilogue, rest: producers
+constexpr int NPROD = 9;         // producer warps: 3, 8..15
+constexpr int NISSUE = R;        // MMA-issuing threads: one per output row (lane 0 of warps 0 and 2)
 constexpr int MAX_AS = 4, MAX_WS = 16;
 constexpr int BATCH = 4;         // producer items (32 entries x 8 channels) in flight per warp
 constexpr int BAR_BYTES = 512;   // a_full/a_empty [MAX_AS], w_full/w_empty [MAX_WS], acc_full/acc_empty [2], TMEM pointer
@@ -57,6 +58,11 @@ __host__ __device__ inline int x_of_entry(int p, int x0, int stride, int dil) {
 }
 // output channels padded to the MMA's N granularity
 __host__ __device__ inline int cout_pad(int cout) { return cout <= 16 ? 16 : (cout + 15) / 16 * 16; }
+// Narrow layers (N <= 64) are bound by the MMA *issue* rate (measured ~50 cycles per tcgen05.mma from one thread, whatever
+// N: profiles/r01_ubench_tcgen05_mma_issue.txt), so they fold the hi / lo weight images into ONE operand of 2N rows:
+//   D[:, 0:2N] += A_hi x [B_hi ; B_lo]      (N' = 2N)        D[:, 0:N] += A_lo x B_hi
+// two instructions per product instead of three; the epilogue adds the two column blocks.
+__host__ __device__ inline bool fold_hi_lo(int CoutP) { return CoutP <= 64; }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -129,6 +135,7 @@ __host__ __device__ inline SmemMap smem_map(int E, int CoutP) {
 }  // namespace um
 
 // UMMA weight image: [16-channel chunk c][tap][hi | lo][8-channel plane kc][f (CoutP)][8 x bf16 = 16 bytes]
+// (narrow layers: [chunk][tap][plane][hi f.. | lo f..][16 bytes], see fold_hi_lo)
 __global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned char* __restrict__ packed, int Cin, int Cout,
                                          int CoutP, int nChunks16) {
   const long long total = (long long)nChunks16 * 9 * CoutP * 8;   // (c, tap, f, channel pair)
@@ -147,12 +154,19 @@ __global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned c
     c3::split_pair(a, b, hi, lo);
     const int wt = 64 * CoutP;
     unsigned char* tile = packed + ((size_t)c * 9 + tap) * wt;
-    const int off = (j >> 2) * (CoutP * 16) + f * 16 + (j & 3) * 4;
-    *reinterpret_cast<uint32_t*>(tile + off) = hi;
-    *reinterpret_cast<uint32_t*>(tile + wt / 2 + off) = lo;
+    if (um::fold_hi_lo(CoutP)) {   // [8-channel plane][hi rows | lo rows][16 B]
+      const int off = (j >> 2) * (2 * CoutP * 16) + f * 16 + (j & 3) * 4;
+      *reinterpret_cast<uint32_t*>(tile + off) = hi;
+      *reinterpret_cast<uint32_t*>(tile + CoutP * 16 + off) = lo;
+    } else {                       // [hi | lo][8-channel plane][rows][16 B]
+      const int off = (j >> 2) * (CoutP * 16) + f * 16 + (j & 3) * 4;
+      *reinterpret_cast<uint32_t*>(tile + off) = hi;
+      *reinterpret_cast<uint32_t*>(tile + wt / 2 + off) = lo;
+    }
   }
 }
 
+template <bool FOLD>
 __global__ void __launch_bounds__(um::NTHREADS, 1)
     conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
                         const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
@@ -176,14 +190,14 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
   if (tid == 0) {
     for (int i = 0; i < AS; ++i) {
       mbar_init(a_full + 8 * i, NPROD);
-      mbar_init(a_empty + 8 * i, 1);
+      mbar_init(a_empty + 8 * i, NISSUE);
     }
     for (int i = 0; i < WS; ++i) {
       mbar_init(w_full + 8 * i, 1);
-      mbar_init(w_empty + 8 * i, 1);
+      mbar_init(w_empty + 8 * i, NISSUE);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(acc_full + 8 * i, 1);
+      mbar_init(acc_full + 8 * i, NISSUE);
       mbar_init(acc_empty + 8 * i, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -197,56 +211,60 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ============================ MMA issuer (one thread) ============================
+  if (warp == 0 || warp == 2) {
+    // ============================ MMA issuers: lane 0 of warp 0 (output row 0) and of warp 2 (row 1) ============================
+    // A single thread sustains one tcgen05.mma per ~50-100 cycles whatever N (profiles/r01_ubench_tcgen05_mma_issue.txt),
+    // below the tensor pipe's 64 cycles at N = 128 once waits and commits are added -- so each output row (its own
+    // accumulator, no ordering between the two) gets its own issuing thread; every stage barrier collects both commits.
     if (lane == 0) {
+      const int r = warp >> 1;
       // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), K-major both, N >> 3 @17, M >> 4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CoutP >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
-      const uint32_t a_lbo = (uint32_t)E * 16u, b_lbo = (uint32_t)CoutP * 16u;
-      // the issue loop is the one serial resource of the CTA: ring positions / parities are running counters (no
-      // divisions) and the 18 tap offsets live in registers (the tap loop is fully unrolled)
-      uint32_t a_off[9][R];
+      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CoutP >> 2) << 17) | ((uint32_t)(MT >> 4) << 24);
+      const uint32_t a_lbo = (uint32_t)E * 16u, b_lbo = (uint32_t)(FOLD ? 2 * CoutP : CoutP) * 16u;
+      const uint32_t row_cols = (uint32_t)(FOLD ? 2 * CoutP : CoutP);   // TMEM columns per output row
+      // ring positions / parities are running counters (no divisions); descriptor low words (address >> 4) of the nine
+      // taps live in registers (the tap loop is fully unrolled), the high words are constants
+      uint32_t a_off[9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          a_off[tap][r] = (uint32_t)((slot_of(r, tap / 3, stride, dil) * PW + tap_xoff(tap % 3, stride, dil)) * 16);
+        a_off[tap] = (uint32_t)((slot_of(r, tap / 3, stride, dil) * PW + tap_xoff(tap % 3, stride, dil)) * 16) >> 4;
       const uint64_t desc_hi_a = ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
       const uint64_t desc_hi_b = ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
-      auto adesc = [&](uint32_t addr) { return desc_hi_a | (uint64_t)((addr >> 4) & 0x3FFFu); };
-      auto bdesc = [&](uint32_t addr) { return desc_hi_b | (uint64_t)((addr >> 4) & 0x3FFFu); };
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, acc = 0, accph = 0, j = 0;
-      const uint32_t w_base = s_base + (uint32_t)sm.w_off, w_half = (uint32_t)(sm.w_tile / 2);
+      const uint32_t a_lo16 = (uint32_t)sm.a_lo >> 4, a_stage16 = (uint32_t)sm.a_stage >> 4, s_base16 = s_base >> 4;
+      const uint32_t w_base16 = (s_base + (uint32_t)sm.w_off) >> 4, w_tile16 = (uint32_t)sm.w_tile >> 4, w_half16 = w_tile16 >> 1;
       for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
         if (j >= (uint32_t)nacc) mbar_wait(acc_empty + 8 * acc, accph ^ 1);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d0 = tmem_base + acc * (uint32_t)(R * CoutP);
+        const uint32_t d = tmem_base + (acc * (uint32_t)R + (uint32_t)r) * row_cols;
         for (int c = 0; c < nChunks; ++c) {
           mbar_wait(a_full + 8 * as, aph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_st = s_base + as * (uint32_t)sm.a_stage;
+          const uint32_t a_st16 = s_base16 + as * a_stage16;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(w_full + 8 * ws, wph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t w_st = w_base + ws * (uint32_t)sm.w_tile;
-            const uint64_t b_hi = bdesc(w_st), b_lo = bdesc(w_st + w_half);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const uint32_t a_addr = a_st + a_off[tap][r];
-              const uint64_t a_hi = adesc(a_addr), a_lo = adesc(a_addr + (uint32_t)sm.a_lo);
-              const uint32_t d = d0 + (uint32_t)(r * CoutP);
+            const uint32_t w16 = w_base16 + ws * w_tile16;
+            const uint64_t a_hi = desc_hi_a | (uint64_t)(a_st16 + a_off[tap]), a_lo = desc_hi_a | (uint64_t)(a_st16 + a_off[tap] + a_lo16);
+            const uint64_t b_hi = desc_hi_b | (uint64_t)w16;
+            if (FOLD) {
+              umma_bf16(d, a_hi, b_hi, idesc2, (tap == 0 && c == 0) ? 0u : 1u);   // [hi*hi | hi*lo]
+              umma_bf16(d, a_lo, b_hi, idesc, 1u);                                // += lo*hi into the first block
+            } else {
+              const uint64_t b_lo = desc_hi_b | (uint64_t)(w16 + w_half16);
               umma_bf16(d, a_hi, b_lo, idesc, (tap == 0 && c == 0) ? 0u : 1u);
               umma_bf16(d, a_lo, b_hi, idesc, 1u);
               umma_bf16(d, a_hi, b_hi, idesc, 1u);
             }
-            umma_commit(w_empty + 8 * ws);       // weight stage free once these MMAs have read it
+            umma_commit(w_empty + 8 * ws);       // weight stage free once both rows' MMAs have read it
             if (++ws == (uint32_t)WS) { ws = 0; wph ^= 1; }
           }
           umma_commit(a_empty + 8 * as);         // input stage free
           if (++as == (uint32_t)AS) { as = 0; aph ^= 1; }
         }
-        umma_commit(acc_full + 8 * acc);         // this tile's accumulators are complete
+        umma_commit(acc_full + 8 * acc);         // this row's accumulator is complete
         if (++acc == (uint32_t)nacc) { acc = 0; accph ^= 1; }
       }
     }
@@ -268,6 +286,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
   } else if (warp >= 4 && warp < 8) {
     // ============================ epilogue (TMEM lanes 32*(warp&3) .. +31 = pixels of the M tile) ============================
     const int q = warp & 3;
+    const uint32_t row_cols = (uint32_t)(FOLD ? 2 * CoutP : CoutP);
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
       const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
@@ -279,11 +298,18 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       for (int r = 0; r < R; ++r) {
         const int y = ty * R + r;
         const bool okp = y < OH && xx < OW;
-        const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + acc * (uint32_t)(R * CoutP) + (uint32_t)(r * CoutP);
+        const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + acc * (uint32_t)R * row_cols + (uint32_t)r * row_cols;
 #pragma unroll 1
         for (int nc = 0; nc < CoutP / 16; ++nc) {
           uint32_t v[16];
           tmem_ld16(t0 + (uint32_t)(nc * 16), v);
+          if (FOLD) {   // second column block: the hi * lo term
+            uint32_t v2[16];
+            tmem_ld16(t0 + (uint32_t)(CoutP + nc * 16), v2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (out_mode == 0) {
             float* on = out + (size_t)n * out_bs + (size_t)y * OW + xx;
@@ -318,8 +344,8 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       if (lane == 0) mbar_arrive(acc_empty + 8 * acc);   // TMEM reads of this accumulator are done (wait::ld above)
     }
   } else {
-    // ============================ input producers (warps 2, 3, 8..15) ============================
-    const int pw = warp < 4 ? warp - 2 : warp - 6;
+    // ============================ input producers (warps 3, 8..15) ============================
+    const int pw = warp < 4 ? 0 : warp - 7;   // warp 3 -> 0, warps 8..15 -> 1..8
     const int G = (E + 31) / 32, nItems = 2 * G;       // item = (32 entries, 8-channel plane)
     uint32_t a_cnt = 0;
     for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
@@ -403,20 +429,28 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   const int OH = stride == 2 ? (H - 1) / 2 + 1 : H, OW = stride == 2 ? (W - 1) / 2 + 1 : W;
   static int configured = 0;
   if (configured < sm.total) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(conv3x3_umma_kernel): %s", cudaGetErrorString(e));
     configured = sm.total;
   }
-  const int nacc = 2 * R * CoutP <= 512 ? 2 : 1;   // double-buffered accumulators when they fit the 512 TMEM columns
+  const int row_cols = fold_hi_lo(CoutP) ? 2 * CoutP : CoutP;   // TMEM columns per output row
+  const int nacc = 2 * R * row_cols <= 512 ? 2 : 1;   // double-buffered accumulators when they fit the 512 TMEM columns
   int cols = 32;
-  while (cols < nacc * R * CoutP) cols *= 2;
+  while (cols < nacc * R * row_cols) cols *= 2;
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
   const long long numTiles = (long long)N * tilesX * tilesY;
   const int cap = tuning().conv_grid_cap > 0 ? tuning().conv_grid_cap : kNumSMs;
   const unsigned grid = (unsigned)(numTiles < cap ? numTiles : cap);
-  conv3x3_umma_kernel<<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout, CoutP,
-                                                        nChunks, slope, tilesX, tilesY, (int)numTiles, stride, dil, out_mode,
-                                                        cols, nacc);
+  if (fold_hi_lo(CoutP))
+    conv3x3_umma_kernel<true><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout,
+                                                                CoutP, nChunks, slope, tilesX, tilesY, (int)numTiles, stride,
+                                                                dil, out_mode, cols, nacc);
+  else
+    conv3x3_umma_kernel<false><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout,
+                                                                 CoutP, nChunks, slope, tilesX, tilesY, (int)numTiles, stride,
+                                                                 dil, out_mode, cols, nacc);
   return check_launch("conv3x3_umma_kernel");
 }
 
