@@ -145,6 +145,20 @@ MFN_API int mfn_warp_mask_forward_tc(const float* x, const float* flow_coarse, c
                                      int F, int upsample_factor, float flow_scale, float level_stride, float leaky_slope,
                                      int border_mode, void* stream);
 
+/* Same operator through linearity (inference): because all nine taps share one offset per pixel, the deformable
+ * convolution equals bilinear re-sampling of the PLAIN 3x3 convolution Y = conv(x, weight) wherever the nine samples fall
+ * inside the image.  Three launches: Y on the tensor cores (packed_weight = mfn_conv3x3_pack_weights(weight)), the fused
+ * re-sampling epilogue, and the tap-by-tap kernel over the list of pixels whose warped centre is within two pixels of the
+ * border (where MFN_BORDER_* rules are not linear).  workspace: caller-owned, mfn_warp_resample_workspace_bytes() bytes,
+ * 16-byte aligned.  Results equal mfn_warp_mask_forward up to fp32 rounding (tests: 1e-4). */
+MFN_API long long mfn_warp_resample_workspace_bytes(int N, int F, int H, int W);
+MFN_API int mfn_warp_mask_forward_resample(const float* x, const float* flow_coarse, const float* mask_coarse,
+                                           const float* weight, const void* packed_weight, const float* bias,
+                                           const float* tradeoff, void* workspace, float* out, float* flow_up_out,
+                                           float* mask_up_out, int N, int C, int H, int W, int F, int upsample_factor,
+                                           float flow_scale, float level_stride, float leaky_slope, int border_mode,
+                                           void* stream);
+
 /* Backward of mfn_warp_mask_forward.
  *   in : grad_out (N,F,H,W); out (forward result); conv_out (saved); x; flow_up (N,2,H,W, the forward's
  *        flow_up_out); mask_up (N,1,H,W) or NULL; weight

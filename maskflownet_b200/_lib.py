@@ -26,6 +26,7 @@ SIGNATURES = {
     "mfn_deformable_conv_backward": [_f] * 8 + [_i] * 6 + [_f],
     "mfn_warp_mask_forward": [_f] * 10 + [_i] * 6 + [_fl, _fl, _fl, _i, _f],
     "mfn_warp_mask_forward_tc": [_f] * 10 + [_i] * 6 + [_fl, _fl, _fl, _i, _f],
+    "mfn_warp_mask_forward_resample": [_f] * 11 + [_i] * 6 + [_fl, _fl, _fl, _i, _f],
     "mfn_warp_mask_backward": [_f] * 14 + [_i] * 5 + [_fl, _fl, _fl, _i, _f],
     "mfn_upsample_forward": [_f, _f, _i, _i, _i, _i, _fl, _f],
     "mfn_upsample_backward": [_f, _f, _i, _i, _i, _i, _fl, _f],
@@ -66,6 +67,8 @@ def lib() -> ctypes.CDLL:
         L.mfn_launch_count.restype = ctypes.c_ulonglong
         L.mfn_conv3x3_packed_bytes.restype = ctypes.c_longlong
         L.mfn_conv3x3_packed_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.mfn_warp_resample_workspace_bytes.restype = ctypes.c_longlong
+        L.mfn_warp_resample_workspace_bytes.argtypes = [ctypes.c_int] * 4
         for name, argtypes in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = argtypes

@@ -60,6 +60,15 @@ __device__ __forceinline__ Axis make_axis(float c, int n) {
   return a;
 }
 
+// Pixels whose nine taps all sample strictly inside the image (both border rules reduce to plain bilinear there): the
+// warped centre lies in [1, H-2] x [1, W-2].  Pixels whose nine taps all fall outside contribute a zero convolution.
+__device__ __forceinline__ bool warp_interior(float h0, float w0, int H, int W) {
+  return h0 >= 1.f && h0 <= (float)(H - 2) && w0 >= 1.f && w0 <= (float)(W - 2);
+}
+__device__ __forceinline__ bool warp_far_outside(float h0, float w0, int H, int W) {
+  return h0 <= -2.f || h0 >= (float)(H + 1) || w0 <= -2.f || w0 >= (float)(W + 1);
+}
+
 // SHARED: all nine taps use the same (dy, dx) (fused warp); otherwise per-tap offsets from `offset` (N,18,H,W).
 // FUSED epilogue operands (mask / tradeoff / conv_out / flow outputs) are only used when SHARED.
 // NT = threads (= pixels) per CTA: 256 for the big levels, 128 / 64 for the small ones so that the grid still covers the GPU
@@ -70,14 +79,23 @@ __global__ void __launch_bounds__(NT, 512 / NT)
                       const float* __restrict__ weight, const float* __restrict__ bias,
                       const float* __restrict__ tradeoff, float* __restrict__ out, float* __restrict__ flow_up_out,
                       float* __restrict__ mask_up_out, float* __restrict__ conv_out, int N, int C, int H, int W,
-                      int F, int up, float flow_scale, float level_stride, float slope) {
+                      int F, int up, float flow_scale, float level_stride, float slope,
+                      const int* __restrict__ pix_list, const int* __restrict__ pix_count) {
   using namespace k3;
   __shared__ __align__(16) float Wt[KC * FT];  // [k][f], f-quads XOR-swizzled by (k & 7)
 
   const int tid = threadIdx.x;
   const long long total = (long long)N * H * W;
-  const long long p = (long long)blockIdx.x * NT + tid;
-  const bool live = p < total;
+  // pix_list: this launch serves only the listed pixels (the border frame left over by warp_resample_kernel); the grid is
+  // sized for the worst case, CTAs beyond the list leave at once
+  long long p = (long long)blockIdx.x * NT + tid;
+  bool live = p < total;
+  if (pix_list) {
+    const int cnt = *pix_count;
+    if ((long long)blockIdx.x * NT >= cnt) return;
+    live = p < cnt;
+    p = live ? pix_list[p] : 0;
+  }
   const int f0 = blockIdx.y * FT;
   const size_t plane = (size_t)H * W;
 
@@ -342,18 +360,19 @@ template <int NT, int FT, int BORDER, bool SHARED>
 static void launch_deform_cfg(const float* x, const float* offset, const float* flow_c, const float* mask_c,
                               const float* weight, const float* bias, const float* tradeoff, float* out, float* fup,
                               float* mup, float* conv_out, int N, int C, int H, int W, int F, int up, float fs, float ls,
-                              float slope, cudaStream_t st) {
+                              float slope, const int* pix_list, const int* pix_count, cudaStream_t st) {
   const long long total = (long long)N * H * W;
   dim3 grid((unsigned)((total + NT - 1) / NT), (unsigned)((F + FT - 1) / FT));
   deform_fwd_kernel<NT, FT, BORDER, SHARED><<<grid, NT, 0, st>>>(x, offset, flow_c, mask_c, weight, bias, tradeoff, out,
-                                                                fup, mup, conv_out, N, C, H, W, F, up, fs, ls, slope);
+                                                                fup, mup, conv_out, N, C, H, W, F, up, fs, ls, slope,
+                                                                pix_list, pix_count);
 }
 
 template <int BORDER, bool SHARED>
 static int launch_deform(const float* x, const float* offset, const float* flow_c, const float* mask_c,
                          const float* weight, const float* bias, const float* tradeoff, float* out, float* fup,
                          float* mup, float* conv_out, int N, int C, int H, int W, int F, int up, float fs, float ls,
-                         float slope, cudaStream_t st) {
+                         float slope, cudaStream_t st, const int* pix_list = nullptr, const int* pix_count = nullptr) {
   // pick (pixels per CTA, output channels per CTA) so that the grid has at least ~3 CTAs per SM; the coarse pyramid
   // levels have only a few thousand pixels
   const long long total = (long long)N * H * W;
@@ -361,7 +380,7 @@ static int launch_deform(const float* x, const float* offset, const float* flow_
   auto ctas = [&](int nt, int ft) { return ((total + nt - 1) / nt) * ((F + ft - 1) / ft); };
 #define MFN_DEFORM_GO(NT_, FT_)                                                                                         \
   launch_deform_cfg<NT_, FT_, BORDER, SHARED>(x, offset, flow_c, mask_c, weight, bias, tradeoff, out, fup, mup, conv_out, \
-                                              N, C, H, W, F, up, fs, ls, slope, st)
+                                              N, C, H, W, F, up, fs, ls, slope, pix_list, pix_count, st)
   if (F > 32 && ctas(256, 64) >= want) MFN_DEFORM_GO(256, 64);
   else if (ctas(256, 32) >= want) MFN_DEFORM_GO(256, 32);
   else if (F > 32 && ctas(128, 64) >= want) MFN_DEFORM_GO(128, 64);
@@ -424,6 +443,137 @@ extern "C" int mfn_warp_mask_forward(const float* x, const float* flow_coarse, c
   return launch_deform<MFN_BORDER_ZERO_CORNER, true>(x, nullptr, flow_coarse, mask_coarse, weight, bias, tradeoff, out,
                                                      flow_up_out, mask_up_out, conv_out, N, C, H, W, F, upsample_factor,
                                                      flow_scale, level_stride, leaky_slope, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3 through linearity.  All nine taps of the reference's deformable convolution share ONE offset per pixel (the flow is
+// `repeat`-ed over the taps, network/MaskFlownet.py:228-232), and bilinear sampling is linear in the image, hence
+//     sum_tap W_tap . S(p + tap + f(p))  =  bilinear sample at p + f(p) of  Y = conv3x3(x, W)   (zero padding)
+// wherever the nine samples fall strictly inside the image.  The fused warp is therefore
+//   (1) Y = plain 3x3 convolution on the tensor cores (conv3x3_umma.cu),
+//   (2) warp_resample_kernel: per pixel up-sample flow / mask, sample Y, + bias, x sigmoid(mask), + trade-off, LeakyReLU,
+//   (3) deform_fwd_kernel over a pixel list: the frame of pixels whose warped centre is within two pixels of the image
+//       border, where the operator's border rules (MFN_BORDER_*) are not linear, computed tap by tap as before (the list is
+//       built by (2) with one atomic per warp; pixels warped far outside are exact zeros and stay in (2)).
+// ---------------------------------------------------------------------------------------------------------
+namespace mfn {
+__global__ void __launch_bounds__(256)
+    warp_resample_kernel(const float* __restrict__ Y, const float* __restrict__ flow_c, const float* __restrict__ mask_c,
+                         const float* __restrict__ bias, const float* __restrict__ tradeoff, float* __restrict__ out,
+                         float* __restrict__ flow_up_out, float* __restrict__ mask_up_out, int* __restrict__ pix_list,
+                         int* __restrict__ pix_count, int N, int H, int W, int F, int up, float flow_scale,
+                         float level_stride, float slope) {
+  const long long total = (long long)N * H * W;
+  const size_t plane = (size_t)H * W;
+  const long long span = (long long)gridDim.x * blockDim.x;
+  // every warp runs the same number of iterations (the border list is built with warp-wide ballots)
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += span) {
+    const long long p = base + threadIdx.x;
+    const bool in_range = p < total;
+    bool border = false;
+    if (in_range) {
+    const int xq = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / plane);
+    const int Hc = H / up, Wc = W / up;
+    const float* fc = flow_c + (size_t)n * 2 * Hc * Wc;
+    const float fy = upsample_at(fc, Hc, Wc, up, y, xq);
+    const float fx = upsample_at(fc + (size_t)Hc * Wc, Hc, Wc, up, y, xq);
+    const float mask_v = mask_c ? upsample_at(mask_c + (size_t)n * Hc * Wc, Hc, Wc, up, y, xq) : 0.f;
+    const size_t pix = (size_t)y * W + xq;
+    if (flow_up_out) {
+      flow_up_out[((size_t)n * 2 + 0) * plane + pix] = fy;
+      flow_up_out[((size_t)n * 2 + 1) * plane + pix] = fx;
+    }
+    if (mask_up_out && mask_c) mask_up_out[(size_t)n * plane + pix] = mask_v;
+    const float dy = __fdiv_rn(__fmul_rn(fy, flow_scale), level_stride);
+    const float dx = __fdiv_rn(__fmul_rn(fx, flow_scale), level_stride);
+    const float h0 = (float)y + dy, w0 = (float)xq + dx;
+    const bool inside = warp_interior(h0, w0, H, W);
+    border = !inside && !warp_far_outside(h0, w0, H, W);   // served by the tap-by-tap pass
+    if (!border) {
+      // far outside: all nine taps are zero (w** = 0 below, indices clamped)
+      const int i0 = inside ? (int)floorf(h0) : 0, j0 = inside ? (int)floorf(w0) : 0;
+      const float lh = h0 - (float)i0, lw = w0 - (float)j0;
+      const float z = inside ? 1.f : 0.f;
+      const float w00 = z * (1.f - lh) * (1.f - lw), w01 = z * (1.f - lh) * lw, w10 = z * lh * (1.f - lw), w11 = z * lh * lw;
+      const float sig = mask_c ? sigmoidf_(mask_v) : 1.f;
+      const float* yp = Y + (size_t)n * F * plane + (size_t)i0 * W + j0;
+      float* op = out + (size_t)n * F * plane + pix;
+      const float* tp = tradeoff ? tradeoff + (size_t)n * F * plane + pix : nullptr;
+#pragma unroll 4
+      for (int f = 0; f < F; ++f) {
+        const float* q = yp + (size_t)f * plane;
+        float v = inside ? w00 * __ldg(q) + w01 * __ldg(q + 1) + w10 * __ldg(q + W) + w11 * __ldg(q + W + 1) : 0.f;
+        if (bias) v += __ldg(bias + f);
+        v *= sig;
+        if (tp) v += __ldg(tp + (size_t)f * plane);
+        op[(size_t)f * plane] = leaky(v, slope);
+      }
+    }
+    }
+    // append the border pixels of this warp to the list: one atomic per warp, lane order kept (neighbours stay together)
+    const unsigned ballot = __ballot_sync(0xffffffffu, border);
+    if (ballot) {
+      const int lane = threadIdx.x & 31;
+      int start = 0;
+      if (lane == 0) start = atomicAdd(pix_count, __popc(ballot));
+      start = __shfl_sync(0xffffffffu, start, 0);
+      if (border) pix_list[start + __popc(ballot & ((1u << lane) - 1u))] = (int)p;
+    }
+  }
+}
+}  // namespace mfn
+
+extern "C" long long mfn_warp_resample_workspace_bytes(int N, int F, int H, int W) {
+  if (N <= 0 || F <= 0 || H <= 0 || W <= 0) return 0;
+  return (long long)N * F * H * W * 4 + 16 + (long long)N * H * W * 4;   // Y | border count | border pixel list
+}
+
+extern "C" int mfn_warp_mask_forward_resample(const float* x, const float* flow_coarse, const float* mask_coarse,
+                                              const float* weight, const void* packed_weight, const float* bias,
+                                              const float* tradeoff, void* workspace, float* out, float* flow_up_out,
+                                              float* mask_up_out, int N, int C, int H, int W, int F, int upsample_factor,
+                                              float flow_scale, float level_stride, float leaky_slope, int border_mode,
+                                              void* stream) {
+  using namespace mfn;
+  MFN_REQUIRE(x && flow_coarse && weight && packed_weight && workspace && out, MFN_ERR_INVALID_ARG,
+              "mfn_warp_mask_forward_resample: null pointer");
+  MFN_REQUIRE(aligned(workspace, 16), MFN_ERR_ALIGNMENT, "mfn_warp_mask_forward_resample: workspace must be 16-byte aligned");
+  MFN_REQUIRE(N > 0 && C > 0 && H >= 4 && W >= 4 && F > 0 && F <= 256, MFN_ERR_INVALID_ARG,
+              "mfn_warp_mask_forward_resample: bad extent (N=%d C=%d H=%d W=%d F=%d)", N, C, H, W, F);
+  MFN_REQUIRE(upsample_factor >= 1 && H % upsample_factor == 0 && W % upsample_factor == 0, MFN_ERR_INVALID_ARG,
+              "mfn_warp_mask_forward_resample: H and W must be multiples of upsample_factor");
+  MFN_REQUIRE(level_stride > 0.f, MFN_ERR_INVALID_ARG, "mfn_warp_mask_forward_resample: level_stride must be positive");
+  MFN_REQUIRE(border_mode == MFN_BORDER_MXNET15 || border_mode == MFN_BORDER_ZERO_CORNER, MFN_ERR_INVALID_ARG,
+              "mfn_warp_mask_forward_resample: unknown border_mode %d", border_mode);
+  MFN_REQUIRE((long long)C * H * W < (1LL << 31) && (long long)F * H * W < (1LL << 31), MFN_ERR_ALIGNMENT,
+              "mfn_warp_mask_forward_resample: extents overflow kernel indexing");
+  float* conv_ws = static_cast<float*>(workspace);
+  int* pix_count = reinterpret_cast<int*>(static_cast<unsigned char*>(workspace) + (size_t)N * F * H * W * 4);
+  int* pix_list = pix_count + 4;
+  // (1) Y = conv3x3(x, W): no bias, no activation
+  int rc = mfn_conv3x3_forward_ex(x, 0, packed_weight, nullptr, conv_ws, 0, N, C, H, W, F, 1, 1, MFN_CONV_OUT_NCHW, 1.0f,
+                                  stream);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t ce = cudaMemsetAsync(pix_count, 0, 16, st);
+  if (ce != cudaSuccess) return fail((int)ce, "mfn_warp_mask_forward_resample: cudaMemsetAsync: %s", cudaGetErrorString(ce));
+  // (2) interior (and far-outside) pixels; builds the border list
+  const long long total = (long long)N * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  warp_resample_kernel<<<(unsigned)blocks, 256, 0, st>>>(conv_ws, flow_coarse, mask_coarse, bias, tradeoff, out, flow_up_out,
+                                                        mask_up_out, pix_list, pix_count, N, H, W, F, upsample_factor,
+                                                        flow_scale, level_stride, leaky_slope);
+  rc = check_launch("warp_resample_kernel");
+  if (rc) return rc;
+  // (3) the border frame, tap by tap
+  if (border_mode == MFN_BORDER_MXNET15)
+    return launch_deform<MFN_BORDER_MXNET15, true>(x, nullptr, flow_coarse, mask_coarse, weight, bias, tradeoff, out, nullptr,
+                                                   nullptr, nullptr, N, C, H, W, F, upsample_factor, flow_scale,
+                                                   level_stride, leaky_slope, st, pix_list, pix_count);
+  return launch_deform<MFN_BORDER_ZERO_CORNER, true>(x, nullptr, flow_coarse, mask_coarse, weight, bias, tradeoff, out,
+                                                     nullptr, nullptr, nullptr, N, C, H, W, F, upsample_factor, flow_scale,
+                                                     level_stride, leaky_slope, st, pix_list, pix_count);
 }
 
 extern "C" int mfn_upsample_forward(const float* in, float* out, int planes, int H, int W, int factor, float scale,

@@ -66,6 +66,7 @@ class DeformParams(nn.Module):
 
 
 class _FlowNetBase(nn.Module):
+    use_resample_warp = True   # inference: K3 through linearity (ops.warp_mask(resample=True)) for layers below 64 channels
     use_tc_conv = True   # inference: decoder / context 3x3 convolutions on the fp32-accurate tensor-core kernel (row N2)
 
     def _packed(self, name):
@@ -274,9 +275,11 @@ class MaskFlownetS(_FlowNetBase):
                 self.event_hook("warp", lvl, 0)
             warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, mask, dp.weight, dp.bias, trade, self.scale,
                                              float(STRIDES[lvl]), 2, SLOPE, self.border_mode,
-                                             # tensor-core variant pays off from 64 channels on (measured: C=32 is gather-bound)
-                                             packed_weight=self._packed(f"deform{lvl}")
-                                             if (self._fast(flow) and dp.weight.shape[0] >= 64) else None)
+                                             # inference: the 32-channel level (gather-bound otherwise) is evaluated through
+                                             # linearity (conv on tcgen05 + re-sampling + border list); >= 64 channels use the
+                                             # gather + mma.sync kernel, whose cost does not depend on the flow field
+                                             packed_weight=self._packed(f"deform{lvl}") if self._fast(flow) else None,
+                                             resample=self.use_resample_warp and dp.weight.shape[0] < 64)
             if self.event_hook is not None:
                 self.event_hook("warp", lvl, 1)
             x = self._corr_block(lvl, c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up])

@@ -238,10 +238,12 @@ class _WarpMaskFn(torch.autograd.Function):
 
 
 def warp_mask(x, flow_coarse, mask_coarse, weight, bias=None, tradeoff=None, scale=20.0, stride=32.0, upsample=2,
-              leaky_slope=0.1, border_mode=BORDER_MXNET15, packed_weight=None):
+              leaky_slope=0.1, border_mode=BORDER_MXNET15, packed_weight=None, resample=False):
     """Fused Upsample(up)(flow, mask) -> deformable conv (all taps offset by flow*scale/stride) -> *sigmoid(mask)
     -> + tradeoff -> LeakyReLU.   Returns (warp, flow_up, mask_up or None).
-    packed_weight (ops.conv3x3_pack(weight)) selects the tensor-core kernel when no gradient is required and F <= 128."""
+    packed_weight (ops.conv3x3_pack(weight)) selects a tensor-core path when no gradient is required: with resample=True
+    the operator is evaluated through linearity (plain 3x3 convolution on tcgen05 + bilinear re-sampling of its output +
+    tap-by-tap border frame, mfn_warp_mask_forward_resample), else the gather-then-mma.sync kernel (F <= 128)."""
     x = _chk(x, "warp_mask.x")
     fc = _chk(flow_coarse, "warp_mask.flow_coarse")
     mc = _chk(mask_coarse, "warp_mask.mask_coarse", optional=True)
@@ -259,6 +261,16 @@ def warp_mask(x, flow_coarse, mask_coarse, weight, bias=None, tradeoff=None, sca
         raise MaskflowError("warp_mask: tradeoff shape mismatch")
     needs_grad = torch.is_grad_enabled() and any(
         z is not None and z.requires_grad for z in (x, fc, mc, w, b, t))
+    if packed_weight is not None and not needs_grad and resample and w.shape[0] <= 256 and H >= 4 and W >= 4:
+        Fo = w.shape[0]
+        out = torch.empty((N, Fo, H, W), device=x.device, dtype=torch.float32)
+        ws = torch.empty(int(_lib.lib().mfn_warp_resample_workspace_bytes(N, Fo, H, W)), device=x.device, dtype=torch.uint8)
+        flow_up = torch.empty((N, 2, H, W), device=x.device, dtype=torch.float32)
+        mask_up = torch.empty((N, 1, H, W), device=x.device, dtype=torch.float32) if mc is not None else None
+        _call("mfn_warp_mask_forward_resample", x.device, _p(x), _p(fc), _p(mc), _p(w), _p(packed_weight), _p(b), _p(t),
+              _p(ws), _p(out), _p(flow_up), _p(mask_up), N, C, H, W, Fo, int(upsample), float(scale), float(stride),
+              float(leaky_slope), int(border_mode))
+        return out, flow_up, mask_up
     if packed_weight is not None and not needs_grad and w.shape[0] <= 128:
         Fo = w.shape[0]
         out = torch.empty((N, Fo, H, W), device=x.device, dtype=torch.float32)

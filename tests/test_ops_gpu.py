@@ -466,6 +466,36 @@ def test_conv3x3_persistent_tile_loop(cap):
     assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max()))
 
 
+@pytest.mark.parametrize("border", [0, 1])
+@pytest.mark.parametrize("N,C,H,W,flow_mag", [(2, 32, 28, 64, 0.3), (1, 64, 30, 132, 1.5), (1, 16, 12, 20, 4.0), (1, 40, 16, 24, 0.0)])
+def test_warp_mask_through_linearity_matches_tap_by_tap(N, C, H, W, flow_mag, border):
+    """mfn_warp_mask_forward_resample (plain conv on tcgen05 + bilinear re-sampling + border frame) == the oracle's
+    deformable convolution, both border rules, flows from sub-pixel to far outside the image."""
+    rng = np.random.default_rng(53)
+    x = feat(rng, (N, C, H, W))
+    w = (rng.standard_normal((C, C, 3, 3)) * np.sqrt(2.0 / (9 * C))).astype(np.float32)
+    b = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    fc = (rng.standard_normal((N, 2, H // 2, W // 2)) * flow_mag).astype(np.float32)
+    mc = rng.standard_normal((N, 1, H // 2, W // 2)).astype(np.float32)
+    t = (rng.standard_normal((N, C, H, W)) * 0.3).astype(np.float32)
+    scale, stride = 20.0, 8.0
+    ref, fup_ref, mup_ref = ops.warp_mask(cu(x), cu(fc), cu(mc), cu(w), cu(b), cu(t), scale, stride, 2, 0.1, border)
+    got, fup, mup = ops.warp_mask(cu(x), cu(fc), cu(mc), cu(w), cu(b), cu(t), scale, stride, 2, 0.1, border,
+                                  packed_weight=ops.conv3x3_pack(cu(w)), resample=True)
+    assert "deform_fwd_kernel" in _lib.last_kernel()        # the border pass ran last
+    tol = 1e-4 * max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) <= tol
+    assert torch.equal(fup, fup_ref) and torch.equal(mup, mup_ref)
+    # and against the CPU oracle directly
+    fu = cref.upsample(fc, 2)
+    off = np.repeat((fu * scale / stride)[:, None], 9, axis=1).reshape(N, 18, H, W)
+    conv = cref.deformable_conv_forward(x, off, w, b, border_mode=border, threads=8)
+    mu = cref.upsample(mc, 2)
+    o = conv * (1.0 / (1.0 + np.exp(-mu))) + t
+    o = np.where(o > 0, o, 0.1 * o)
+    assert np.abs(got.cpu().numpy() - o).max() <= 2e-4 * max(1.0, float(np.abs(o).max()))
+
+
 def test_conv3x3_in_place_concat_block():
     """The dense block: five convolutions reading / writing channel slices of one buffer == torch.cat chain."""
     rng = np.random.default_rng(32)
