@@ -63,6 +63,11 @@ __host__ __device__ inline int cout_pad(int cout) { return cout <= 16 ? 16 : (co
 //   D[:, 0:2N] += A_hi x [B_hi ; B_lo]      (N' = 2N)        D[:, 0:N] += A_lo x B_hi
 // two instructions per product instead of three; the epilogue adds the two column blocks.
 __host__ __device__ inline bool fold_hi_lo(int CoutP) { return CoutP <= 64; }
+// Taps per weight-ring stage (compile-time variants of the kernel).  Both rings are bound by their ROUND-TRIP latency
+// (commit -> mbarrier -> waiting thread wakes -> copy / conversion -> mbarrier -> issuer wakes: ~2 us measured), not by
+// bandwidth: a ring of S stages delivers S stages per round trip.  Narrow layers, whose MMAs per tap are short, therefore
+// move 9 / 3 taps per bulk copy.
+__host__ __device__ inline int taps_per_stage(int CoutP) { return CoutP <= 32 ? 9 : (CoutP <= 64 ? 3 : 1); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -115,7 +120,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 struct SmemMap {
-  int a_lo, a_stage, w_tile, w_off, bar_off, total, AS, WS;
+  int a_lo, a_stage, w_tile, w_stage, w_off, bar_off, total, AS, WS;
 };
 // stage counts from the shared-memory budget: 3 input stages when that still leaves >= 8 weight stages, else 2
 __host__ __device__ inline SmemMap smem_map(int E, int CoutP) {
@@ -124,11 +129,17 @@ __host__ __device__ inline SmemMap smem_map(int E, int CoutP) {
   m.a_stage = 2 * m.a_lo;           // hi + lo
   m.w_tile = 64 * CoutP;            // [hi | lo][2 planes][CoutP][16 B]
   const int budget = 227 * 1024 - BAR_BYTES;
-  m.AS = (3 * m.a_stage + 8 * m.w_tile <= budget) ? 3 : 2;
-  int ws = (budget - m.AS * m.a_stage) / m.w_tile;
+  m.w_stage = taps_per_stage(CoutP) * m.w_tile;
+  // input stages: narrow layers (several taps per weight stage) take 4 when >= 4 weight stages still fit; wide layers keep
+  // the weight ring deep (their weight stages are single taps) and take 3
+  if (taps_per_stage(CoutP) > 1)
+    m.AS = (4 * m.a_stage + 4 * m.w_stage <= budget) ? 4 : ((3 * m.a_stage + 3 * m.w_stage <= budget) ? 3 : 2);
+  else
+    m.AS = (3 * m.a_stage + 8 * m.w_stage <= budget) ? 3 : 2;
+  int ws = (budget - m.AS * m.a_stage) / m.w_stage;
   m.WS = ws > MAX_WS ? MAX_WS : ws;
   m.w_off = m.AS * m.a_stage;
-  m.bar_off = m.w_off + m.WS * m.w_tile;
+  m.bar_off = m.w_off + m.WS * m.w_stage;
   m.total = m.bar_off + BAR_BYTES;
   return m;
 }
@@ -166,7 +177,7 @@ __global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned c
   }
 }
 
-template <bool FOLD>
+template <bool FOLD, int TPS>
 __global__ void __launch_bounds__(um::NTHREADS, 1)
     conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
                         const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
@@ -234,6 +245,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       uint32_t as = 0, aph = 0, ws = 0, wph = 0, acc = 0, accph = 0, j = 0;
       const uint32_t a_lo16 = (uint32_t)sm.a_lo >> 4, a_stage16 = (uint32_t)sm.a_stage >> 4, s_base16 = s_base >> 4;
       const uint32_t w_base16 = (s_base + (uint32_t)sm.w_off) >> 4, w_tile16 = (uint32_t)sm.w_tile >> 4, w_half16 = w_tile16 >> 1;
+      const uint32_t w_stage16 = (uint32_t)sm.w_stage >> 4;
       for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
         if (j >= (uint32_t)nacc) mbar_wait(acc_empty + 8 * acc, accph ^ 1);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -244,9 +256,11 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
           const uint32_t a_st16 = s_base16 + as * a_stage16;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(w_full + 8 * ws, wph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t w16 = w_base16 + ws * w_tile16;
+            if (tap % TPS == 0) {
+              mbar_wait(w_full + 8 * ws, wph);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint32_t w16 = w_base16 + ws * w_stage16 + (uint32_t)(tap % TPS) * w_tile16;
             const uint64_t a_hi = desc_hi_a | (uint64_t)(a_st16 + a_off[tap]), a_lo = desc_hi_a | (uint64_t)(a_st16 + a_off[tap] + a_lo16);
             const uint64_t b_hi = desc_hi_b | (uint64_t)w16;
             if (FOLD) {
@@ -258,8 +272,10 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
               umma_bf16(d, a_lo, b_hi, idesc, 1u);
               umma_bf16(d, a_hi, b_hi, idesc, 1u);
             }
-            umma_commit(w_empty + 8 * ws);       // weight stage free once both rows' MMAs have read it
-            if (++ws == (uint32_t)WS) { ws = 0; wph ^= 1; }
+            if (tap % TPS == TPS - 1) {
+              umma_commit(w_empty + 8 * ws);     // weight stage free once both rows' MMAs have read it
+              if (++ws == (uint32_t)WS) { ws = 0; wph ^= 1; }
+            }
           }
           umma_commit(a_empty + 8 * as);         // input stage free
           if (++as == (uint32_t)AS) { as = 0; aph ^= 1; }
@@ -275,10 +291,10 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       bool wrapped = false;
       for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
         const unsigned char* src = wpack;
-        for (int it = 0; it < nIter; ++it, src += sm.w_tile) {
+        for (int it = 0; it < nIter; it += TPS, src += sm.w_stage) {
           if (wrapped) mbar_wait(w_empty + 8 * ws, wph ^ 1);
-          mbar_arrive_expect_tx(w_full + 8 * ws, (uint32_t)sm.w_tile);
-          bulk_g2s(s_base + (uint32_t)sm.w_off + ws * (uint32_t)sm.w_tile, src, (uint32_t)sm.w_tile, w_full + 8 * ws);
+          mbar_arrive_expect_tx(w_full + 8 * ws, (uint32_t)sm.w_stage);
+          bulk_g2s(s_base + (uint32_t)sm.w_off + ws * (uint32_t)sm.w_stage, src, (uint32_t)sm.w_stage, w_full + 8 * ws);
           if (++ws == (uint32_t)WS) { ws = 0; wph ^= 1; wrapped = true; }
         }
       }
@@ -352,10 +368,90 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
       const int x0 = tx * MT, y0 = ty * R;
       const float* xn = x + (size_t)n * x_bs;
+      // The producers are bound by their own instruction stream (ncu: ~150 integer instructions per item for the tile
+      // geometry), so when a chunk is one batch per warp (the common 2-row, dilation-1 tile) the per-item geometry -- source
+      // offset, validity, destination -- is computed ONCE per tile; per chunk only the channel plane advances.
+      const bool hoist = nItems <= NPROD * BATCH;
+      int goff[BATCH], soff[BATCH];
+      if (hoist) {
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int t = pw + b * NPROD;
+          const int kc = t & 1, e = (t >> 1) * 32 + lane;
+          const int slot = e / PW, pe = e - slot * PW;
+          const int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(pe, x0, stride, dil);
+          const bool act = t < nItems && e < E;
+          const bool ok = act && y >= 0 && y < H && xx >= 0 && xx < W;
+          goff[b] = ok ? y * W + xx : -1;
+          soff[b] = act ? (kc * E + e) * 16 : -1;
+        }
+      }
+      if (hoist) {
+        // chunk loop, software-pipelined over two register sets: the loads of chunk c+1 are in flight while chunk c is
+        // converted (bytes in flight = registers holding loads; one chunk per warp is only 4 KB)
+        auto load_chunk = [&](int c, float (&v)[BATCH][8]) {
+          const float* xc = xn + (size_t)(16 * c) * plane;
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) {
+            const int kc = (pw + b * NPROD) & 1;
+            const int c0 = 16 * c + 8 * kc;
+            const float* src = xc + (size_t)(8 * kc) * plane + (goff[b] >= 0 ? goff[b] : 0);
+            const bool ok = goff[b] >= 0;
+            if (c0 + 8 <= Cin) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                v[b][jj] = ok ? __ldg(src) : 0.f;
+                src += plane;
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                v[b][jj] = (ok && c0 + jj < Cin) ? __ldg(src) : 0.f;
+                src += plane;
+              }
+            }
+          }
+        };
+        auto store_chunk = [&](const float (&v)[BATCH][8]) {
+          const uint32_t as = a_cnt % (uint32_t)AS;
+          if (a_cnt >= (uint32_t)AS) mbar_wait(a_empty + 8 * as, ((a_cnt / (uint32_t)AS) + 1) & 1);
+          unsigned char* a_st = smem + as * sm.a_stage;
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) {
+            if (soff[b] >= 0) {
+              uint4 hi, lo;
+              split_pair(v[b][0], v[b][1], hi.x, lo.x);
+              split_pair(v[b][2], v[b][3], hi.y, lo.y);
+              split_pair(v[b][4], v[b][5], hi.z, lo.z);
+              split_pair(v[b][6], v[b][7], hi.w, lo.w);
+              unsigned char* dst = a_st + soff[b];
+              *reinterpret_cast<uint4*>(dst) = hi;
+              *reinterpret_cast<uint4*>(dst + sm.a_lo) = lo;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + 8 * as);
+          ++a_cnt;
+        };
+        float va[BATCH][8], vb[BATCH][8];
+        load_chunk(0, va);
+        for (int c = 0; c < nChunks; c += 2) {
+          if (c + 1 < nChunks) load_chunk(c + 1, vb);
+          store_chunk(va);
+          if (c + 1 < nChunks) {
+            if (c + 2 < nChunks) load_chunk(c + 2, va);
+            store_chunk(vb);
+          }
+        }
+        continue;   // next tile
+      }
       for (int c = 0; c < nChunks; ++c, ++a_cnt) {
         const uint32_t as = a_cnt % (uint32_t)AS;
         if (a_cnt >= (uint32_t)AS) mbar_wait(a_empty + 8 * as, ((a_cnt / (uint32_t)AS) + 1) & 1);
         unsigned char* a_st = smem + as * sm.a_stage;
+        {
+        }
         for (int k0 = pw; k0 < nItems; k0 += NPROD * BATCH) {
           float v[BATCH][8];
 #pragma unroll
@@ -429,9 +525,11 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   const int OH = stride == 2 ? (H - 1) / 2 + 1 : H, OW = stride == 2 ? (W - 1) / 2 + 1 : W;
   static int configured = 0;
   if (configured < sm.total) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv3x3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+      e = cudaFuncSetAttribute(conv3x3_umma_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_umma_kernel<true, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(conv3x3_umma_kernel): %s", cudaGetErrorString(e));
     configured = sm.total;
   }
@@ -443,14 +541,14 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   const long long numTiles = (long long)N * tilesX * tilesY;
   const int cap = tuning().conv_grid_cap > 0 ? tuning().conv_grid_cap : kNumSMs;
   const unsigned grid = (unsigned)(numTiles < cap ? numTiles : cap);
-  if (fold_hi_lo(CoutP))
-    conv3x3_umma_kernel<true><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout,
-                                                                CoutP, nChunks, slope, tilesX, tilesY, (int)numTiles, stride,
-                                                                dil, out_mode, cols, nacc);
-  else
-    conv3x3_umma_kernel<false><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout,
-                                                                 CoutP, nChunks, slope, tilesX, tilesY, (int)numTiles, stride,
-                                                                 dil, out_mode, cols, nacc);
+#define MFN_UMMA_LAUNCH(FOLD_, TPS_)                                                                                       \
+  conv3x3_umma_kernel<FOLD_, TPS_><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout,  \
+                                                                     CoutP, nChunks, slope, tilesX, tilesY, (int)numTiles,      \
+                                                                     stride, dil, out_mode, cols, nacc)
+  if (taps_per_stage(CoutP) == 9) MFN_UMMA_LAUNCH(true, 9);
+  else if (taps_per_stage(CoutP) == 3) MFN_UMMA_LAUNCH(true, 3);
+  else MFN_UMMA_LAUNCH(false, 1);
+#undef MFN_UMMA_LAUNCH
   return check_launch("conv3x3_umma_kernel");
 }
 
