@@ -149,3 +149,20 @@ def test_multiscale_epe_loss_matches_oracle_and_backprops():
     lr.sum().backward()
     for a, b in zip(gp, rp):
         assert (a.grad.cpu() - b.grad).abs().max().item() < 1e-6
+
+
+@pytest.mark.gpu
+def test_flow_predictor_cuda_graph_equals_eager():
+    """network.FlowPredictor (predict_flow captured in a CUDA graph, static input buffers) returns exactly what the eager
+    call returns, also when it is replayed with new inputs."""
+    torch.manual_seed(3)
+    model = network.MaskFlownetS().cuda().eval()
+    pred = network.FlowPredictor(model)
+    for seed in (0, 1):
+        g = torch.Generator().manual_seed(seed)
+        a = torch.randint(0, 256, (2, 3, 64, 128), generator=g, dtype=torch.uint8).cuda()
+        b = torch.randint(0, 256, (2, 3, 64, 128), generator=g, dtype=torch.uint8).cuda()
+        ref = network.predict_flow(model, a, b).clone()
+        got = pred(a, b).clone()
+        assert torch.equal(ref, got)
+
