@@ -178,10 +178,10 @@ def main():
     def step_resident():
         return network.predict_flow(model, a_d, b_d)
 
-    predictor = network.FlowPredictor(model)   # the user-facing call: predict_flow captured in a CUDA graph
-
     def step_e2e():
-        flow = predictor(a_h, b_h)             # H2D from pinned host memory into the graph's static input buffers
+        x1 = a_h.to(dev, non_blocking=True)    # H2D from pinned host memory
+        x2 = b_h.to(dev, non_blocking=True)
+        flow = network.predict_flow(model, x1, x2)
         out_h.copy_(flow, non_blocking=True)   # D2H of the result
         return flow
 
@@ -267,8 +267,8 @@ def main():
                    "l2": "256 MiB buffer overwritten between steps (inside the timed region, ~0.05 ms/step)",
                    "value_path": "network.predict_flow, eager launches, device-resident inputs, CUDA events around the hot-path "
                                  "kernels inside the timed region",
-                   "e2e_path": "network.FlowPredictor (the same step captured in a CUDA graph), pinned host uint8 in, "
-                               "pinned host fp32 flow out, copies inside the timed region"},
+                   "e2e_path": "network.predict_flow (eager launches), pinned host uint8 in, pinned host fp32 flow out, "
+                               "copies inside the timed region"},
         "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s", "h2d_bytes_per_step": int(a_h.numel() + b_h.numel()),
                 "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": round(ms_e2e / K, 4)},
         "gpu_launches": int(launches),
