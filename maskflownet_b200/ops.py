@@ -414,15 +414,16 @@ def conv3x3_slices(buf_in: torch.Tensor, c_in0: int, Cin: int, packed: torch.Ten
           Cout, int(stride), int(dilation), 1 if depth_to_space else 0, float(leaky_slope))
 
 
-def conv_transpose4x4_pack(weight: torch.Tensor) -> torch.Tensor:
+def conv_transpose4x4_as_conv3x3(weight: torch.Tensor) -> torch.Tensor:
     """nn.ConvTranspose2d(Cin, F, kernel 4, stride 2, pad 1) (the decoder's `upfeat` layers, network/MaskFlownet.py:225 ...)
-    as a 3x3 convolution with 4F outputs + depth-to-space: output pixel (2y+py, 2x+px) only touches inputs (y+dy, x+dx)
-    with dy in {0, -1} (py = 0) or {0, +1} (py = 1), kernel row ky = py + 1 - 2 dy.  Returns the packed 3x3 weights
-    (conv channel (2 py + px) * F + f); the five unused taps of every phase are zero."""
-    w = _chk(weight.detach(), "conv_transpose4x4_pack.weight")       # (Cin, F, 4, 4)
+    re-arranged as the weight (4F, Cin, 3, 3) of a 3x3 convolution followed by depth-to-space: output pixel (2y+py, 2x+px)
+    only touches inputs (y+dy, x+dx) with dy in {0, -1} (py = 0) or {0, +1} (py = 1), through kernel row ky = py + 1 - 2 dy
+    (likewise columns).  Conv channel (2 py + px) * F + f; the five unused taps of every phase are zero.  Pure tensor
+    algebra (any device) -- checked on the CPU in tests/test_host_logic.py."""
+    w = weight.detach()
     Cin, F, kh, kw = w.shape
     if (kh, kw) != (4, 4):
-        raise MaskflowError("conv_transpose4x4_pack: weight must be (Cin, F, 4, 4)")
+        raise MaskflowError("conv_transpose4x4_as_conv3x3: weight must be (Cin, F, 4, 4)")
     w3 = torch.zeros((4 * F, Cin, 3, 3), device=w.device, dtype=torch.float32)
     for py in range(2):
         for px in range(2):
@@ -431,7 +432,12 @@ def conv_transpose4x4_pack(weight: torch.Tensor) -> torch.Tensor:
                 for dx in ((0, -1) if px == 0 else (0, 1)):
                     ky, kx = py + 1 - 2 * dy, px + 1 - 2 * dx
                     w3[ph * F:(ph + 1) * F, :, dy + 1, dx + 1] = w[:, :, ky, kx].t()
-    return conv3x3_pack(w3)
+    return w3
+
+
+def conv_transpose4x4_pack(weight: torch.Tensor) -> torch.Tensor:
+    """Packed weight image of conv_transpose4x4_as_conv3x3(weight) for conv3x3_slices(..., depth_to_space=True)."""
+    return conv3x3_pack(conv_transpose4x4_as_conv3x3(_chk(weight, "conv_transpose4x4_pack.weight")))
 
 
 def conv3x3(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor], Cout: int, leaky_slope: float = 0.1,
