@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
                         const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
                         int OH, int OW, int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int numTiles,
-                        int stride, int dil, int out_mode, int tmem_cols, int nacc) {
+                        int stride, int dil, int out_mode, int tmem_cols, int nacc, int ext) {
   using namespace um;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nslots = n_slots(stride, dil), PW = row_pitch(stride, dil), E = nslots * PW;
@@ -366,7 +366,9 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     uint32_t a_cnt = 0;
     for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
       const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
-      const int x0 = tx * MT, y0 = ty * R;
+      // ext = 1: "full" convolution -- the output grid is the input grid extended by one pixel on every side
+      // (OH = H + 2, OW = W + 2; output (y, x) sits at input position (y - 1, x - 1)); used by K3 through linearity
+      const int x0 = tx * MT - ext, y0 = ty * R - ext;
       const float* xn = x + (size_t)n * x_bs;
       // The producers are bound by their own instruction stream (ncu: ~150 integer instructions per item for the tile
       // geometry), so when a chunk is one batch per warp (the common 2-row, dilation-1 tile) the per-item geometry -- source
@@ -515,14 +517,15 @@ int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int C
 // returns -1 when the shape does not fit this kernel (caller falls back to the mma.sync kernel)
 int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
                         long long out_bs, int N, int Cin, int H, int W, int Cout, int stride, int dil, int out_mode,
-                        float slope, cudaStream_t st) {
+                        float slope, cudaStream_t st, int ext) {
   using namespace um;
   if (Cout > 256 || (stride != 1 && !(stride == 2 && dil == 1))) return -1;
+  if (ext != 0 && !(ext == 1 && stride == 1 && dil == 1 && out_mode == 0)) return -1;
   const int CoutP = um::cout_pad(Cout), nChunks = (Cin + 15) / 16;
   const int E = n_slots(stride, dil) * row_pitch(stride, dil);
   const SmemMap sm = smem_map(E, CoutP);
   if (sm.WS < 2 || E * 16 > 0x3FFF * 16) return -1;
-  const int OH = stride == 2 ? (H - 1) / 2 + 1 : H, OW = stride == 2 ? (W - 1) / 2 + 1 : W;
+  const int OH = stride == 2 ? (H - 1) / 2 + 1 : H + 2 * ext, OW = stride == 2 ? (W - 1) / 2 + 1 : W + 2 * ext;
   static int configured = 0;
   if (configured < sm.total) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
@@ -544,7 +547,7 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
 #define MFN_UMMA_LAUNCH(FOLD_, TPS_)                                                                                       \
   conv3x3_umma_kernel<FOLD_, TPS_><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout,  \
                                                                      CoutP, nChunks, slope, tilesX, tilesY, (int)numTiles,      \
-                                                                     stride, dil, out_mode, cols, nacc)
+                                                                     stride, dil, out_mode, cols, nacc, ext)
   if (taps_per_stage(CoutP) == 9) MFN_UMMA_LAUNCH(true, 9);
   else if (taps_per_stage(CoutP) == 3) MFN_UMMA_LAUNCH(true, 3);
   else MFN_UMMA_LAUNCH(false, 1);

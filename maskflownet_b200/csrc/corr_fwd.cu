@@ -1015,6 +1015,10 @@ template <int MD>
 static int launch_mma(const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,
                       float slope, cudaStream_t st) {
   const bool vec = (W % 4 == 0) && aligned(d2, 16) && aligned(d1, 16);
+  if (C <= 32 && tuning().corr_tma) {   // TMA-in / TMA-out pipeline (corr_tma.cu); -1 = shape or alignment does not fit
+    const int rc = launch_corr_tma(MD, d1, d2, out, N, C, H, W, obs, slope, st);
+    if (rc != -1) return rc;
+  }
   if (C <= 32 && !tuning().corr_disable_ring) {
     if (tuning().corr_ring_th == 8)
       return vec ? launch_mma_ring_impl<MD, true, 8>(d1, d2, out, N, C, H, W, obs, slope, st)

@@ -51,6 +51,6 @@ long long conv3x3_umma_packed_bytes(int Cin, int Cout);
 int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int Cout, cudaStream_t st);
 int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
                         long long out_bs, int N, int Cin, int H, int W, int Cout, int stride, int dil, int out_mode,
-                        float slope, cudaStream_t st);
+                        float slope, cudaStream_t st, int ext = 0);
 
 }  // namespace mfn

@@ -525,7 +525,9 @@ __global__ void __launch_bounds__(256)
 
 extern "C" long long mfn_warp_resample_workspace_bytes(int N, int F, int H, int W) {
   if (N <= 0 || F <= 0 || H <= 0 || W <= 0) return 0;
-  return (long long)N * F * H * W * 4 + 16 + (long long)N * H * W * 4;   // Y | border count | border pixel list
+  const long long list_path = (long long)N * F * H * W * 4 + 16 + (long long)N * H * W * 4;   // Y | border count | border pixel list
+  const long long lin_path = mfn::warp_lin_workspace_bytes(N, F, H, W);                          // Yext | Rrow | Rcol | T
+  return list_path > lin_path ? list_path : lin_path;
 }
 
 extern "C" int mfn_warp_mask_forward_resample(const float* x, const float* flow_coarse, const float* mask_coarse,
@@ -547,6 +549,12 @@ extern "C" int mfn_warp_mask_forward_resample(const float* x, const float* flow_
               "mfn_warp_mask_forward_resample: unknown border_mode %d", border_mode);
   MFN_REQUIRE((long long)C * H * W < (1LL << 31) && (long long)F * H * W < (1LL << 31), MFN_ERR_ALIGNMENT,
               "mfn_warp_mask_forward_resample: extents overflow kernel indexing");
+  if (tuning().warp_lin) {   // exact evaluation through linearity for every pixel (warp_lin.cu); -1 = extended conv does not fit
+    const int rl = launch_warp_lin(x, flow_coarse, mask_coarse, weight, packed_weight, bias, tradeoff, workspace, out, flow_up_out,
+                                   mask_up_out, N, C, H, W, F, upsample_factor, flow_scale, level_stride, leaky_slope, border_mode,
+                                   as_stream(stream));
+    if (rl != -1) return rl;
+  }
   float* conv_ws = static_cast<float*>(workspace);
   int* pix_count = reinterpret_cast<int*>(static_cast<unsigned char*>(workspace) + (size_t)N * F * H * W * 4);
   int* pix_list = pix_count + 4;

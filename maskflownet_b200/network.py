@@ -66,7 +66,7 @@ class DeformParams(nn.Module):
 
 
 class _FlowNetBase(nn.Module):
-    use_resample_warp = True   # inference: K3 through linearity (ops.warp_mask(resample=True)) for layers below 64 channels
+    use_resample_warp = True   # inference: K3 through linearity (ops.warp_mask(resample=True)) at every level
     use_tc_conv = True   # inference: decoder / context 3x3 convolutions on the fp32-accurate tensor-core kernel (row N2)
 
     def _packed(self, name):
@@ -275,11 +275,10 @@ class MaskFlownetS(_FlowNetBase):
                 self.event_hook("warp", lvl, 0)
             warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, mask, dp.weight, dp.bias, trade, self.scale,
                                              float(STRIDES[lvl]), 2, SLOPE, self.border_mode,
-                                             # inference: the 32-channel level (gather-bound otherwise) is evaluated through
-                                             # linearity (conv on tcgen05 + re-sampling + border list); >= 64 channels use the
-                                             # gather + mma.sync kernel, whose cost does not depend on the flow field
+                                             # inference: every level is evaluated exactly through linearity (extended 3x3
+                                             # convolution on tcgen05 + bilinear re-sampling + border-band tables, warp_lin.cu)
                                              packed_weight=self._packed(f"deform{lvl}") if self._fast(flow) else None,
-                                             resample=self.use_resample_warp and dp.weight.shape[0] < 64)
+                                             resample=self.use_resample_warp)
             if self.event_hook is not None:
                 self.event_hook("warp", lvl, 1)
             x = self._corr_block(lvl, c1[lvl - 1], warp, [c1[lvl - 1], feat, flow_up])
@@ -339,8 +338,10 @@ class MaskFlownet(_FlowNetBase):
         c4 = self._pyramid(c40, "xyz")
         flow = flows_s[0]
         dp = self.deform6
+        fast = self._fast(flow)
         warp, _, _ = ops.warp_mask(c2[5], flow, None, dp.weight, dp.bias, None, self.scale, float(STRIDES[6]), 1,
-                                   SLOPE, self.border_mode)
+                                   SLOPE, self.border_mode, packed_weight=self._packed("deform6") if fast else None,
+                                   resample=self.use_resample_warp)
         x = self._dense(6, torch.cat([self._corr(c1[5], warp), self._corr(c3[5], c4[5]), flow], dim=1))
         flow = flow + self._heads(6, x, False)[0]
         flows = [flow]
@@ -348,7 +349,9 @@ class MaskFlownet(_FlowNetBase):
             feat = self._upfeat(lvl, x)
             dp = getattr(self, f"deform{lvl}")
             warp, flow_up, _ = ops.warp_mask(c2[lvl - 1], flow, None, dp.weight, dp.bias, None, self.scale,
-                                             float(STRIDES[lvl]), 2, SLOPE, self.border_mode)
+                                             float(STRIDES[lvl]), 2, SLOPE, self.border_mode,
+                                             packed_weight=self._packed(f"deform{lvl}") if fast else None,
+                                             resample=self.use_resample_warp)
             x = self._dense(lvl, torch.cat([c1[lvl - 1], feat, self._corr(c1[lvl - 1], warp),
                                             self._corr(c3[lvl - 1], c4[lvl - 1]), flow_up, flows_s[i + 1]], dim=1))
             flow = flow_up + self._heads(lvl, x, False)[0]

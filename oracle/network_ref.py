@@ -1,4 +1,5 @@
-"""CPU restatement of the reference's MaskFlownet_S forward (network/MaskFlownet.py:197-315).  TEST INFRASTRUCTURE ONLY.
+"""CPU restatement of the reference's MaskFlownet_S forward (network/MaskFlownet.py:197-315) and of the full cascade
+MaskFlownet.hybrid_forward (:443-545).  TEST INFRASTRUCTURE ONLY.
 
 Purpose: (1) checker for the product graph maskflownet_b200.network.MaskFlownetS (tests, smoke()), (2) the CPU arm of
 bench.py (`cpu_baseline` and `--impl reference`): the reference's own CPU path cannot run here (MXNet is not installable,
@@ -27,7 +28,8 @@ def _t(a):
 
 
 def maskflownet_s_forward(params: Dict[str, torch.Tensor], im1: torch.Tensor, im2: torch.Tensor, scale: float = 20.0,
-                          threads: int = 1, border_mode: int = 0, want_cascade_inputs: bool = False, taps=None):
+                          threads: int = 1, border_mode: int = 0, want_cascade_inputs: bool = False, taps=None,
+                          want_srcs: bool = False):
     """params: name -> CPU float tensor; im1, im2: (N,3,H,W) CPU float tensors (already /255 and centralised).
     Returns (predictions[5], [sigmoid(mask2)], c40 or None), numpy-free torch tensors on CPU."""
     P = {k: v.detach().cpu().float() for k, v in params.items()}
@@ -94,7 +96,70 @@ def maskflownet_s_forward(params: Dict[str, torch.Tensor], im1: torch.Tensor, im
         mask0 = torch.sigmoid(_t(cref.upsample(mask.numpy(), 4))) - 0.5
         warped = _t(cref.reconstruction2d(im2.numpy(), cref.upsample(flow.numpy(), 4) * scale))
         c40 = torch.cat([warped, mask0], dim=1)
+    if want_srcs:   # what the cascade consumes (MaskFlownet.py:304-314); note c2s levels 2 and 3 are IMAGE-1 features (:306)
+        c2s = [c2[0], c1[1], c1[2], c2[3], c2[4], c2[5]]
+        c30 = torch.cat([im1, torch.zeros_like(im1[:, :1])], dim=1)
+        return preds, [torch.sigmoid(mask)], (c1, c2s, flows, c30, c40)
     return preds, [torch.sigmoid(mask)], c40
+
+
+def maskflownet_forward(params: Dict[str, torch.Tensor], im1: torch.Tensor, im2: torch.Tensor, scale: float = 20.0,
+                        threads: int = 1, border_mode: int = 0):
+    """The cascade (reference class MaskFlownet, network/MaskFlownet.py:443-545).  params: head parameters under
+    `MaskFlownet_S.<name>`, the cascade's own under `<name>`.  Returns (predictions[5], [flow2[:, 0:1]])."""
+    head = {k[len("MaskFlownet_S."):]: v for k, v in params.items() if k.startswith("MaskFlownet_S.")}
+    P = {k: v.detach().cpu().float() for k, v in params.items() if not k.startswith("MaskFlownet_S.")}
+    _, _, srcs = maskflownet_s_forward(head, im1, im2, scale, threads, border_mode, want_cascade_inputs=True, want_srcs=True)
+    c1, c2, flows_s, c30, c40 = srcs
+
+    def conv(name, x, stride=1, pad=1, dil=1, act=True):
+        y = tF.conv2d(x, P[name + ".weight"], P[name + ".bias"], stride, pad, dil)
+        return tF.leaky_relu(y, SLOPE) if act else y
+
+    def pyramid(x):   # conv{L}x (stride 2), conv{L}y, conv{L}z  (:445-457)
+        feats = []
+        for lvl in range(1, 7):
+            x = conv(f"conv{lvl}x", x, stride=2)
+            x = conv(f"conv{lvl}y", x)
+            x = conv(f"conv{lvl}z", x)
+            feats.append(x)
+        return feats
+
+    def corr(a, b):   # md = 2 -> 25 channels (:440-441), LeakyReLU (:467 ...)
+        c = _t(cref.correlation_forward(a.numpy(), b.numpy(), pad_size=2, max_displacement=2, threads=threads))
+        return tF.leaky_relu(c, SLOPE)
+
+    def deform(lvl, x, flow):   # deformL(c2L, repeat(flow*scale/stride, 9)) + LeakyReLU, no mask (:465-466 ...)
+        off = (flow * scale / STRIDES[lvl]).unsqueeze(1).repeat(1, 9, 1, 1, 1).reshape(flow.shape[0], 18, *flow.shape[2:])
+        b = P.get(f"deform{lvl}.bias")
+        w = _t(cref.deformable_conv_forward(x.numpy(), off.numpy(), P[f"deform{lvl}.weight"].numpy(),
+                                            None if b is None else b.numpy(), border_mode=border_mode, threads=threads))
+        return tF.leaky_relu(w, SLOPE)
+
+    def dense(lvl, x):
+        for i in range(5):
+            x = torch.cat([conv(f"conv{lvl}_{i}", x), x], dim=1)
+        return x
+
+    c3, c4 = pyramid(c30), pyramid(c40)
+    flow = flows_s[0]
+    x = dense(6, torch.cat([corr(c1[5], deform(6, c2[5], flow)), corr(c3[5], c4[5]), flow], dim=1))
+    flow = flow + conv("pred_flow6", x, act=False)
+    flows = [flow]
+    for i, lvl in enumerate((5, 4, 3, 2)):
+        feat = tF.leaky_relu(tF.conv_transpose2d(x, P[f"upfeat{lvl}.weight"], P[f"upfeat{lvl}.bias"], 2, 1), SLOPE)
+        flow_up = _t(cref.upsample(flow.numpy(), 2))
+        cu_ = corr(c1[lvl - 1], deform(lvl, c2[lvl - 1], flow_up))
+        cv_ = corr(c3[lvl - 1], c4[lvl - 1])
+        x = dense(lvl, torch.cat([c1[lvl - 1], feat, cu_, cv_, flow_up, flows_s[i + 1]], dim=1))
+        flow = flow_up + conv(f"pred_flow{lvl}", x, act=False)
+        flows.append(flow)
+    y = x
+    for i, d in zip(range(1, 7), (1, 2, 4, 8, 16, 1)):
+        y = conv(f"dc_conv{i}", y, pad=d, dil=d)
+    flow = flow + conv("dc_conv7", y, act=False)
+    flows[-1] = flow
+    return [f * scale for f in flows], [flow[:, 0:1]]
 
 
 def predict_flow(params, img1_u8: torch.Tensor, img2_u8: torch.Tensor, threads: int = 1) -> torch.Tensor:

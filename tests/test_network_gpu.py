@@ -74,6 +74,35 @@ def test_predict_flow_pipeline():
     assert (flow.cpu() - ref).abs().max().item() < 5e-3
 
 
+def test_cascade_matches_reference_graph_fixture():
+    """network.MaskFlownet == the reference's own MaskFlownet.hybrid_forward (network/MaskFlownet.py:443-545) run unchanged
+    through the shim with the oracle's operators (tests/golden/net_ref_graph_cascade.npz): pins the dual pyramid, the md=2
+    correlations, deform6 and the c2s quirk (:306).  Bound: 1e-4 relative to the flow scale (x20) = 2e-3 px."""
+    d = np.load(os.path.join(G, "net_ref_graph_cascade.npz"))
+    model = _named_model(network.MaskFlownet)
+    assert sum(p.numel() for p in model.parameters()) == int(d["n_params"])
+    im1, im2 = seeded_images()
+    with torch.no_grad():
+        preds, vis, _ = model(im1.cuda(), im2.cuda())
+    errs = {}
+    for k, p in zip(("pred6", "pred5", "pred4", "pred3", "pred2"), preds):
+        errs[k] = float(np.abs(p.cpu().numpy() - d[k]).max())
+    print("cascade max abs errors (px):", errs)
+    assert max(errs.values()) < 2e-3, errs
+    assert np.abs(vis[0].cpu().numpy() - d["vis"]).max() < 1e-4
+
+
+def test_cascade_matches_oracle_network_fresh_inputs():
+    model = _named_model(network.MaskFlownet)
+    a1, a2 = seeded_images(seed=11, n=2, h=64, w=128)
+    params = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    with torch.no_grad():
+        preds = model(a1.cuda(), a2.cuda())[0]
+        ref = network_ref.maskflownet_forward(params, a1, a2, threads=8)[0]
+    for p, r in zip(preds, ref):
+        assert (p.cpu() - r).abs().max().item() < 2e-3
+
+
 def test_cascade_forward_runs_and_uses_md2_kernels():
     model = network.MaskFlownet().cuda().eval()
     a1, a2 = seeded_images(seed=7, n=1, h=64, w=128)

@@ -467,10 +467,13 @@ def test_conv3x3_persistent_tile_loop(cap):
 
 
 @pytest.mark.parametrize("border", [0, 1])
-@pytest.mark.parametrize("N,C,H,W,flow_mag", [(2, 32, 28, 64, 0.3), (1, 64, 30, 132, 1.5), (1, 16, 12, 20, 4.0), (1, 40, 16, 24, 0.0)])
-def test_warp_mask_through_linearity_matches_tap_by_tap(N, C, H, W, flow_mag, border):
-    """mfn_warp_mask_forward_resample (plain conv on tcgen05 + bilinear re-sampling + border frame) == the oracle's
-    deformable convolution, both border rules, flows from sub-pixel to far outside the image."""
+@pytest.mark.parametrize("lin", [1, 0])
+@pytest.mark.parametrize("N,C,H,W,flow_mag", [(2, 32, 28, 64, 0.3), (1, 64, 30, 132, 1.5), (1, 16, 12, 20, 4.0), (1, 40, 16, 24, 0.0),
+                                              (2, 128, 14, 32, 0.6), (1, 96, 28, 64, 2.5), (1, 8, 4, 6, 0.8)])
+def test_warp_mask_through_linearity_matches_tap_by_tap(N, C, H, W, flow_mag, border, lin):
+    """mfn_warp_mask_forward_resample == the oracle's deformable convolution, both border rules, flows from sub-pixel to far
+    outside the image.  lin=1: every pixel through linearity (extended tcgen05 convolution + band tables, warp_lin.cu);
+    lin=0: the round-1 path (plain convolution + re-sampling + tap-by-tap border list)."""
     rng = np.random.default_rng(53)
     x = feat(rng, (N, C, H, W))
     w = (rng.standard_normal((C, C, 3, 3)) * np.sqrt(2.0 / (9 * C))).astype(np.float32)
@@ -480,9 +483,14 @@ def test_warp_mask_through_linearity_matches_tap_by_tap(N, C, H, W, flow_mag, bo
     t = (rng.standard_normal((N, C, H, W)) * 0.3).astype(np.float32)
     scale, stride = 20.0, 8.0
     ref, fup_ref, mup_ref = ops.warp_mask(cu(x), cu(fc), cu(mc), cu(w), cu(b), cu(t), scale, stride, 2, 0.1, border)
-    got, fup, mup = ops.warp_mask(cu(x), cu(fc), cu(mc), cu(w), cu(b), cu(t), scale, stride, 2, 0.1, border,
-                                  packed_weight=ops.conv3x3_pack(cu(w)), resample=True)
-    assert "deform_fwd_kernel" in _lib.last_kernel()        # the border pass ran last
+    _lib.set_tuning("warp_lin", lin)
+    try:
+        got, fup, mup = ops.warp_mask(cu(x), cu(fc), cu(mc), cu(w), cu(b), cu(t), scale, stride, 2, 0.1, border,
+                                      packed_weight=ops.conv3x3_pack(cu(w)), resample=True)
+        last = _lib.last_kernel()
+    finally:
+        _lib.set_tuning("warp_lin", 1)
+    assert ("warp_lin_kernel" if lin else "deform_fwd_kernel") in last
     tol = 1e-4 * max(1.0, float(ref.abs().max()))
     assert float((got - ref).abs().max()) <= tol
     assert torch.equal(fup, fup_ref) and torch.equal(mup, mup_ref)
@@ -494,6 +502,26 @@ def test_warp_mask_through_linearity_matches_tap_by_tap(N, C, H, W, flow_mag, bo
     o = conv * (1.0 / (1.0 + np.exp(-mu))) + t
     o = np.where(o > 0, o, 0.1 * o)
     assert np.abs(got.cpu().numpy() - o).max() <= 2e-4 * max(1.0, float(np.abs(o).max()))
+
+
+@pytest.mark.parametrize("border", [0, 1])
+def test_warp_through_linearity_band_cases(border):
+    """Flows chosen so that tap rows / columns land exactly in the one-pixel bands where the MXNet-1.5 rule departs from
+    zero-extended bilinear sampling (h in (-1,0), (H-1,H)), on band edges (integers), in corners and far outside; without
+    mask / trade-off / bias (the cascade's call, network/MaskFlownet.py:465)."""
+    rng = np.random.default_rng(77)
+    N, C, H, W = 1, 16, 8, 12
+    x = feat(rng, (N, C, H, W))
+    w = (rng.standard_normal((C, C, 3, 3)) * np.sqrt(2.0 / (9 * C))).astype(np.float32)
+    scale, stride = 20.0, 4.0     # offset = flow * 5
+    vals = np.array([0.0, 0.1, -0.1, 0.2, -0.2, 0.3, -0.35, 0.5, -0.5, 1.0, -1.0, 1.7, -1.9, 2.4, -2.4, 5.0], np.float32)
+    for trial in range(4):
+        fc = rng.choice(vals, size=(N, 2, H, W)).astype(np.float32)
+        ref, _, _ = ops.warp_mask(cu(x), cu(fc), None, cu(w), None, None, scale, stride, 1, 0.1, border)
+        got, _, _ = ops.warp_mask(cu(x), cu(fc), None, cu(w), None, None, scale, stride, 1, 0.1, border,
+                                  packed_weight=ops.conv3x3_pack(cu(w)), resample=True)
+        assert "warp_lin_kernel" in _lib.last_kernel()
+        assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), trial
 
 
 def test_conv3x3_in_place_concat_block():
