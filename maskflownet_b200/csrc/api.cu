@@ -49,6 +49,7 @@ extern "C" int mfn_set_tuning(const char* key, int value) {
   if (!strcmp(key, "corr_grid_cap")) mfn::tuning().corr_grid_cap = value;
   else if (!strcmp(key, "corr_disable_ring")) mfn::tuning().corr_disable_ring = value;
   else if (!strcmp(key, "warp_lin")) mfn::tuning().warp_lin = value;
+  else if (!strcmp(key, "corr_rb")) mfn::tuning().corr_rb = value;
   else if (!strcmp(key, "corr_tma")) mfn::tuning().corr_tma = value;
   else if (!strcmp(key, "corr_dbg")) mfn::tuning().corr_dbg = value;
   else if (!strcmp(key, "corr_ring_th")) mfn::tuning().corr_ring_th = value;

@@ -20,6 +20,7 @@ struct Tuning {
   int conv_grid_cap = 0;      // persistent tcgen05 convolution: CTAs (0 = one per SM); tests force long per-CTA tile runs
   int conv_umma_min_w = 1;    // narrower images stay on the mma.sync kernel (a 128-pixel M tile would be mostly padding)
   int corr_ring_th = 8;       // tile height of the strip-marching kernel: 4 (8 warps, 2 CTAs/SM) or 8 (16 warps, 1 CTA/SM)
+  int corr_rb = 1;            // 1: C > 32 correlations run on the row-block kernel (corr_rb.cu); 2: also C <= 32 when the TMA kernel declines; 0: chunked tile kernel
   int corr_tma = 1;           // 1: C <= 32 correlations run on the TMA pipeline kernel (corr_tma.cu) when the shape fits
   int warp_lin = 1;           // 1: mfn_warp_mask_forward_resample evaluates every pixel through linearity (warp_lin.cu); 0: border list
   int corr_dbg = 0;           // profiling aid for the ring kernel: 2 = producers idle, 4 = no epilogue, 8 = no MMA (results invalid)
@@ -37,11 +38,30 @@ static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<u
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function AND per device (a process may drive several GPUs: ops._call
+// switches the device per tensor): remember the largest opt-in per device, re-issue it when a launch needs more.
+struct SmemOptIn {
+  int bytes[64] = {};
+};
+template <typename K>
+static inline cudaError_t ensure_dyn_smem(K kernel, int bytes, SmemOptIn& st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  if (dev >= 0 && dev < 64 && st.bytes[dev] >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) st.bytes[dev] = bytes;
+  return e;
+}
+
 // warp_lin.cu: K3 through linearity, exact for both border rules; -1 = the extended tcgen05 convolution does not fit
 long long warp_lin_workspace_bytes(int N, int F, int H, int W);
 int launch_warp_lin(const float* x, const float* flow_c, const float* mask_c, const float* weight, const void* packed_weight,
                     const float* bias, const float* tradeoff, void* workspace, float* out, float* fup, float* mup, int N,
                     int C, int H, int W, int F, int up, float fs, float ls, float slope, int border_mode, cudaStream_t st);
+
+// corr_rb.cu: returns -1 when no configuration fits shared memory
+int launch_corr_rb(int md, const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,
+                   float slope, cudaStream_t st);
 
 // corr_tma.cu: returns -1 when the shape / alignment does not fit (caller falls back to the LDG kernels)
 int launch_corr_tma(int md, const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,

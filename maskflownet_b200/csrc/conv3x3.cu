@@ -259,12 +259,10 @@ static int launch_conv_impl(const float* x, long long x_bs, const unsigned char*
   const int tilesX = (W + TW - 1) / TW, tilesY = (H + WR - 1) / WR;
   const int in_stage = PT ? 2 * WR * TW * PXB : 2 * (WR + 2) * HWP * PXB;
   const int smem = 2 * in_stage + WSTAGES * 2 * CoutP * PXB;
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e =
-        cudaFuncSetAttribute(conv3x3_mma_kernel<WC, NTN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static SmemOptIn opt;
+  {
+    const cudaError_t e = ensure_dyn_smem(conv3x3_mma_kernel<WC, NTN, PT>, smem, opt);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(conv3x3_mma_kernel): %s", cudaGetErrorString(e));
-    configured = smem;
   }
   const unsigned grid = (unsigned)((long long)N * tilesX * tilesY);
   conv3x3_mma_kernel<WC, NTN, PT><<<grid, NTHREADS, smem, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, Cout,

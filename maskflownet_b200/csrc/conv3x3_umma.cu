@@ -79,14 +79,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// Bounded wait (2^28 polls, each of which suspends for the hardware's try_wait window): a protocol bug fails the launch
+// with a trap instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
+  uint32_t done = 0, spins = 0;
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+    if (!done && ++spins > (1u << 28)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -526,15 +529,12 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   const SmemMap sm = smem_map(E, CoutP);
   if (sm.WS < 2 || E * 16 > 0x3FFF * 16) return -1;
   const int OH = stride == 2 ? (H - 1) / 2 + 1 : H + 2 * ext, OW = stride == 2 ? (W - 1) / 2 + 1 : W + 2 * ext;
-  static int configured = 0;
-  if (configured < sm.total) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv3x3_umma_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv3x3_umma_kernel<true, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+  static SmemOptIn opt0, opt3, opt9;
+  {
+    cudaError_t e = ensure_dyn_smem(conv3x3_umma_kernel<false, 1>, sm.total, opt0);
+    if (e == cudaSuccess) e = ensure_dyn_smem(conv3x3_umma_kernel<true, 3>, sm.total, opt3);
+    if (e == cudaSuccess) e = ensure_dyn_smem(conv3x3_umma_kernel<true, 9>, sm.total, opt9);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(conv3x3_umma_kernel): %s", cudaGetErrorString(e));
-    configured = sm.total;
   }
   const int row_cols = fold_hi_lo(CoutP) ? 2 * CoutP : CoutP;   // TMEM columns per output row
   const int nacc = 2 * R * row_cols <= 512 ? 2 : 1;   // double-buffered accumulators when they fit the 512 TMEM columns

@@ -102,12 +102,10 @@ static int launch_corr_bwd(const float* go, const float* fo, const float* d1, co
   const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
   const unsigned tiles = (unsigned)((long long)N * tilesX * tilesY);
   const int smem = (int)sizeof(float) * (D * TH * TW + CK * (TH + 2 * MD) * (TW + 8));
-  static bool done = false;
-  if (!done) {
-    cudaFuncSetAttribute(corr_bwd_kernel<MD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(corr_bwd_kernel<MD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    done = true;
-  }
+  static SmemOptIn optA, optB;
+  cudaError_t ae = ensure_dyn_smem(corr_bwd_kernel<MD, false>, smem, optA);
+  if (ae == cudaSuccess) ae = ensure_dyn_smem(corr_bwd_kernel<MD, true>, smem, optB);
+  if (ae != cudaSuccess) return fail((int)ae, "cudaFuncSetAttribute(corr_bwd_kernel): %s", cudaGetErrorString(ae));
   if (g1) {
     corr_bwd_kernel<MD, false><<<tiles, NT, smem, st>>>(go, fo, d2, g1, N, C, H, W, obs, slope);
     const int rc = check_launch("corr_bwd_kernel<sideA>");

@@ -188,14 +188,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // bounded: traps instead of hanging
+  uint32_t ok, spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+    if (!ok && ++spins > (1u << 28)) __trap();
   } while (!ok);
 }
 
@@ -948,10 +949,10 @@ static int launch_simt(const float* d1, const float* d2, float* out, int N, int 
   const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
   const long long tiles = (long long)N * tilesX * tilesY;
   const size_t smem = sizeof(float) * CK * (TH * TW + (TH + 2 * MD) * (TW + 8));
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(corr_simt_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
+  static SmemOptIn opt;
+  {
+    const cudaError_t e = ensure_dyn_smem(corr_simt_kernel<MD>, (int)smem, opt);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_simt_kernel): %s", cudaGetErrorString(e));
   }
   corr_simt_kernel<MD><<<(unsigned)tiles, 64 * G, smem, st>>>(d1, d2, out, N, C, H, W, obs, slope);
   return check_launch(MD == 4 ? "corr_simt_kernel<4>" : "corr_simt_kernel<2>");
@@ -964,11 +965,10 @@ static int launch_mma_impl(const float* d1, const float* d2, float* out, int N, 
   const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
   const long long tiles = (long long)N * tilesX * tilesY;
   const int smem = smem_bytes(MD);
-  static bool attr_done = false;  // per template instantiation; the attribute is per-function (all devices share the module)
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(corr_mma_kernel<MD, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static SmemOptIn opt;   // per template instantiation, per device
+  {
+    const cudaError_t e = ensure_dyn_smem(corr_mma_kernel<MD, VEC>, smem, opt);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_mma_kernel): %s", cudaGetErrorString(e));
-    attr_done = true;
   }
   const int cap = tuning().corr_grid_cap > 0 ? tuning().corr_grid_cap : kNumSMs;
   const int grid = (int)(tiles < cap ? tiles : cap);
@@ -987,11 +987,10 @@ static int launch_mma_ring_impl(const float* d1, const float* d2, float* out, in
   constexpr int NTHREADS = 64 * TH;
   const int smem = r4::smem_bytes(MD, TH);
   const int ovec = ((W % 4) == 0 && (obs % 4) == 0 && aligned(out, 16)) ? 1 : 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(corr_mma_ring_kernel<MD, VEC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static SmemOptIn opt;
+  {
+    const cudaError_t e = ensure_dyn_smem(corr_mma_ring_kernel<MD, VEC, TH>, smem, opt);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_mma_ring_kernel): %s", cudaGetErrorString(e));
-    attr_done = true;
   }
   // strip-aligned work pieces: T = tiles per CTA if all SMs were used; each (n, x-strip) column is cut into
   // ceil(tilesY / T) pieces, one CTA per piece (e.g. level 2 of configs[1]: 64 strips x 2 pieces of 7 tiles = 128 CTAs)
@@ -1017,6 +1016,10 @@ static int launch_mma(const float* d1, const float* d2, float* out, int N, int C
   const bool vec = (W % 4 == 0) && aligned(d2, 16) && aligned(d1, 16);
   if (C <= 32 && tuning().corr_tma) {   // TMA-in / TMA-out pipeline (corr_tma.cu); -1 = shape or alignment does not fit
     const int rc = launch_corr_tma(MD, d1, d2, out, N, C, H, W, obs, slope, st);
+    if (rc != -1) return rc;
+  }
+  if (tuning().corr_rb && (C > 32 || !tuning().corr_tma || tuning().corr_rb > 1)) {   // row-block kernel (corr_rb.cu): all channels resident
+    const int rc = launch_corr_rb(MD, d1, d2, out, N, C, H, W, obs, slope, st);
     if (rc != -1) return rc;
   }
   if (C <= 32 && !tuning().corr_disable_ring) {

@@ -458,13 +458,10 @@ static int launch_corr_tma_impl(const float* d1, const float* d2, float* out, in
   rc = make_map(&tmo, out, dout, sout, bo, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
 
-  static bool attr_done[64] = {};   // per device (the attribute is per function AND per device)
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(corr_tma_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  static SmemOptIn opt;
+  {
+    const cudaError_t e = ensure_dyn_smem(corr_tma_kernel<MD>, SMEM_BYTES, opt);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(corr_tma_kernel): %s", cudaGetErrorString(e));
-    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const int tilesX = (W + TW - 1) / TW, Gs = (H + UR - 1) / UR;
   const long long units = (long long)N * tilesX * Gs;

@@ -265,12 +265,10 @@ static int launch_warp_mma(const float* x, const float* flow_c, const float* mas
   const int FP = cout_pad(F), nChunks = (C + 31) / 32;
   const int tilesX = (W + TW - 1) / TW, tilesY = (H + WR - 1) / WR;
   const int smem = 2 * (2 * WR * TW * PXB) + WSTAGES * 2 * FP * PXB;
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e =
-        cudaFuncSetAttribute(warp_mma_kernel<WC, NTN, BORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static SmemOptIn opt;
+  {
+    const cudaError_t e = ensure_dyn_smem(warp_mma_kernel<WC, NTN, BORDER>, smem, opt);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(warp_mma_kernel): %s", cudaGetErrorString(e));
-    configured = smem;
   }
   const unsigned grid = (unsigned)((long long)N * tilesX * tilesY);
   warp_mma_kernel<WC, NTN, BORDER><<<grid, NTHREADS, smem, st>>>(x, flow_c, mask_c, wpack, bias, tradeoff, out, fup, mup,

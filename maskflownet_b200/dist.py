@@ -48,6 +48,8 @@ class GradBucket:
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
+        if any(p.device != dev or p.dtype != torch.float32 for p in self.params):
+            raise ValueError("GradBucket: all parameters must be float32 on one device")
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         off = 0
@@ -55,19 +57,53 @@ class GradBucket:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
+        self._views = [p.grad for p in self.params]
+
     def zero_(self):
+        """The ONLY supported way to clear the gradients: `optimizer.zero_grad()` / `model.zero_grad()` default to
+        set_to_none=True, which would drop the views into the bucket."""
         self.flat.zero_()
+
+    def rebind_(self):
+        """Re-attach the gradient views (after an accidental zero_grad(set_to_none=True)); gradients accumulated into
+        detached tensors in the meantime are copied into the bucket."""
+        for p, v in zip(self.params, self._views):
+            if p.grad is None:
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+
+    def _check_aliasing(self):
+        for p, v in zip(self.params, self._views):
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                raise RuntimeError("GradBucket: a parameter's .grad no longer aliases the bucket (zero_grad(set_to_none=True)?); "
+                                   "use bucket.zero_() to clear gradients, or bucket.rebind_() to re-attach")
+
+    class _Handle:
+        """async all-reduce in flight: wait() completes it AND applies the 1/global_batch scale."""
+
+        def __init__(self, work, flat, scale):
+            self.work, self.flat, self.scale = work, flat, scale
+
+        def wait(self):
+            if self.work is not None:
+                self.work.wait()
+                self.work = None
+                self.flat.mul_(self.scale)
 
     def allreduce_(self, global_batch: int, async_op: bool = False):
         """Sum over ranks, then scale by 1/global_batch (MXNet Trainer.step(batch_size) semantics: per-sample losses are
-        summed, the optimizer rescales by 1/batch_size)."""
-        work = None
+        summed, the optimizer rescales by 1/batch_size).  async_op=True returns a handle whose wait() finishes the
+        reduction and applies the scale."""
+        self._check_aliasing()
+        scale = 1.0 / float(global_batch)
         if dist.is_initialized() and dist.get_world_size() > 1:
             work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
             if async_op:
-                return work
-        self.flat.mul_(1.0 / float(global_batch))
-        return work
+                return GradBucket._Handle(work, self.flat, scale)
+        self.flat.mul_(scale)
+        return None
 
 
 def max_over_ranks(value: float, device) -> float:

@@ -11,8 +11,9 @@ unrolled reference code: one loop over pyramid levels in which
     Upsample(4) + GridGenerator + BilinearSampler + sigmoid-0.5 + concat (:308-313)
                                                                     -> one launch of ops.image_warp_concat (K5)
 
-The dense 3x3 convolutions (about 98 % of the FLOPs) are outside the hot-path scope and stay on
-cuDNN through torch.nn.functional.  Sub-module names equal the reference's gluon prefixes (conv1a ... deform5, conv5f,
+The dense 3x3 / transposed convolutions (about 98 % of the FLOPs; row N2) run on the tcgen05 / TMEM
+kernel of csrc/conv3x3_umma.cu at inference (`_fast`): f32 in / out, bf16 hi+lo split operands, fp32 accumulation; with
+gradients enabled they go through torch.nn.functional (autograd).  Sub-module names equal the reference's gluon prefixes (conv1a ... deform5, conv5f,
 dc_conv7 ...) so that shipped .params checkpoints map by name (maskflownet_b200.params).
 
 All flows are (y, x)-ordered and in units of pixels/scale, as in the reference (pipeline.py:105, MaskFlownet.py:69).
@@ -239,7 +240,9 @@ class MaskFlownetS(_FlowNetBase):
     def _corr_block(self, lvl, f1, f2, extras: List[torch.Tensor]):
         N, _, H, W = f1.shape
         D = (2 * self.md + 1) ** 2
-        if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
+        # same gate as every other layer (_fast): with grad enabled and ANY trainable parameter the autograd operators
+        # run, so a frozen pyramid + trainable decoder still trains conv{lvl}_0..4
+        if not self._fast(f1):
             corr = ops.correlation(f1, f2, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE)
             return self._dense(lvl, torch.cat([corr] + extras, dim=1) if extras else corr)
         tot = D + sum(e.shape[1] for e in extras)
@@ -381,7 +384,9 @@ def predict_flow(net: nn.Module, img1_u8: torch.Tensor, img2_u8: torch.Tensor) -
 class FlowPredictor:
     """predict_flow captured in a CUDA graph: one graph per input shape, static uint8 input buffers, one cudaGraphLaunch
     per call (the eager step is ~115 dependent launches; the graph removes the launch gaps between them).
-    Weights are read through the packed images cached in the model: call invalidate() after changing parameters."""
+    Weights are read through the packed images cached in the model: call invalidate() after changing parameters.
+    The returned tensor is the graph's STATIC output buffer: the next call overwrites it -- clone() it (or copy it to the
+    host) before calling again if the previous result is still needed."""
 
     def __init__(self, net: nn.Module, warmup: int = 2):
         self.net, self.warmup, self._graphs = net, warmup, {}
@@ -415,3 +420,64 @@ class FlowPredictor:
         graph.replay()
         return out
 
+
+
+class PipelinedFlowPredictor:
+    """Serving loop around FlowPredictor for HOST buffers: every call enqueues (asynchronously)
+        pinned uint8 images --H2D (copy stream)--> staging --D2D--> graph inputs --graph replay--> flow --D2D--> staging
+        --D2H (copy stream)--> pinned fp32 flow
+    with `depth` staging slots, so the H2D copy of request i+1 and the D2H copy of result i-1 run under the forward of
+    request i (PCIe is full duplex; 22 MB in / 29 MB out per batch of 8 at 1024x448 take ~0.4 / ~0.5 ms of a ~9 ms forward).
+    Results are complete after synchronize() (or after waiting on the event infer() returns)."""
+
+    def __init__(self, net: nn.Module, depth: int = 2):
+        self.pred = FlowPredictor(net)
+        self.depth = depth
+        self._slots = None
+        self._i = 0
+
+    def _setup(self, img1, dev):
+        shp = tuple(img1.shape)
+        N, _, H, W = shp
+        self.h2d, self.d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._slots = []
+        for _ in range(self.depth):
+            self._slots.append({
+                "in1": torch.empty(shp, dtype=img1.dtype, device=dev), "in2": torch.empty(shp, dtype=img1.dtype, device=dev),
+                "out": torch.empty((N, 2, H, W), dtype=torch.float32, device=dev),
+                "ev_h2d": torch.cuda.Event(), "ev_in_free": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
+                "ev_out_free": torch.cuda.Event(), "used": False})
+
+    @torch.no_grad()
+    def infer(self, img1_host: torch.Tensor, img2_host: torch.Tensor, out_host: torch.Tensor) -> torch.cuda.Event:
+        dev = next(self.pred.net.parameters()).device
+        if self._slots is None:
+            self._setup(img1_host, dev)
+        s = self._slots[self._i % self.depth]
+        self._i += 1
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self.h2d):
+            if s["used"]:
+                self.h2d.wait_event(s["ev_in_free"])
+            s["in1"].copy_(img1_host, non_blocking=True)
+            s["in2"].copy_(img2_host, non_blocking=True)
+            s["ev_h2d"].record(self.h2d)
+        cur.wait_event(s["ev_h2d"])
+        flow = self.pred(s["in1"], s["in2"])          # D2D into the graph's static inputs + replay
+        s["ev_in_free"].record(cur)
+        if s["used"]:
+            cur.wait_event(s["ev_out_free"])
+        s["out"].copy_(flow, non_blocking=True)
+        s["ev_out"].record(cur)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(s["ev_out"])
+            out_host.copy_(s["out"], non_blocking=True)
+            s["ev_out_free"].record(self.d2h)
+        s["used"] = True
+        return s["ev_out_free"]
+
+    def synchronize(self) -> None:
+        if self._slots is not None:
+            self.h2d.synchronize()
+            self.d2h.synchronize()
+        torch.cuda.current_stream().synchronize()

@@ -39,6 +39,14 @@ def _chk(t: Optional[torch.Tensor], name: str, optional: bool = False) -> Option
     return t.contiguous()
 
 
+def _no_grad_path(name: str, *tensors) -> None:
+    """Forward-only kernels: refuse to silently cut the autograd graph: raise when grad mode is on and any
+    operand requires grad."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise MaskflowError(f"{name} is forward-only (no backward kernel): call it under torch.no_grad() or detach the "
+                            f"operands -- an operand requires grad")
+
+
 def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -330,6 +338,7 @@ def upsample(x, factor: int, scale: float = 1.0):
 def grid_generator_warp(flow_xy):
     """MXNet F.GridGenerator(data=flow, transform_type='warp'); flow channels are (x, y)."""
     f = _chk(flow_xy, "grid_generator_warp.flow")
+    _no_grad_path("grid_generator_warp", f)
     N, two, H, W = f.shape
     if two != 2:
         raise MaskflowError("grid_generator_warp: flow must have 2 channels")
@@ -341,6 +350,7 @@ def grid_generator_warp(flow_xy):
 def bilinear_sampler(data, grid):
     """MXNet F.BilinearSampler(data, grid) (forward only)."""
     d, g = _chk(data, "bilinear_sampler.data"), _chk(grid, "bilinear_sampler.grid")
+    _no_grad_path("bilinear_sampler", d, g)
     N, C, H, W = d.shape
     if g.shape[0] != N or g.shape[1] != 2:
         raise MaskflowError("bilinear_sampler: grid must be (N,2,OH,OW)")
@@ -360,6 +370,7 @@ def image_warp_concat(im1, im2, flow_q, mask_q, scale=20.0, want_c30=True):
     i2 = _chk(im2, "image_warp_concat.im2")
     i1 = _chk(im1, "image_warp_concat.im1", optional=not want_c30)
     fq, mq = _chk(flow_q, "image_warp_concat.flow_q"), _chk(mask_q, "image_warp_concat.mask_q")
+    _no_grad_path("image_warp_concat", i1, i2, fq, mq)
     N, Ci, H, W = i2.shape
     if fq.shape != (N, 2, H // 4, W // 4) or mq.shape != (N, 1, H // 4, W // 4) or H % 4 or W % 4:
         raise MaskflowError("image_warp_concat: flow_q/mask_q must be (N,2|1,H/4,W/4)")
@@ -408,6 +419,7 @@ def conv3x3_slices(buf_in: torch.Tensor, c_in0: int, Cin: int, packed: torch.Ten
     if buf_in.data_ptr() == buf_out.data_ptr() and not (c_out0 + Cout <= c_in0 or c_in0 + Cin <= c_out0):
         raise MaskflowError("conv3x3_slices: input and output slices overlap")
     b = _chk(bias, "conv3x3_slices.bias", optional=True)
+    _no_grad_path("conv3x3_slices", buf_in, b)
     xin = ctypes.c_void_p(buf_in.data_ptr() + 4 * c_in0 * H * W)
     xout = ctypes.c_void_p(buf_out.data_ptr() + 4 * c_out0 * OH * OW)
     _call("mfn_conv3x3_forward_ex", buf_in.device, xin, Cti * H * W, _p(packed), _p(b), xout, Cto * OH * OW, N, Cin, H, W,

