@@ -13,7 +13,9 @@
 
 namespace mfn {
 namespace k2 {
-constexpr int TH = 4, TW = 32, CK = 8, NT = 256;
+// CTA = 4 rows x 32 pixels; thread = one 4-pixel quad x CPT channels: every G quad read from shared memory feeds CPT
+// channels (the round-1 kernel, one channel per thread, moved 5.3 bytes of shared memory per FMA; this one 2.3).
+constexpr int TH = 4, TW = 32, CPT = 4, CK = 8 * CPT, NT = 256;
 }
 
 template <int MD, bool SIDE_B>
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(k2::NT)
     Gt[e] = v;
   }
 
-  const int qx = tid & 7, r = (tid >> 3) & 3, cc = tid >> 5;  // 8 quads x 4 rows x 8 channels
+  const int qx = tid & 7, r = (tid >> 3) & 3, cg = tid >> 5;  // 8 quads x 4 rows x 8 channel groups of CPT
   const float* Xn = X + (size_t)n * C * plane;
   const float inv = 1.f / (float)C;
   for (int c0 = 0; c0 < C; c0 += CK) {
@@ -67,29 +69,51 @@ __global__ void __launch_bounds__(k2::NT)
       Xs[e] = (c < C && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(Xn + (size_t)c * plane + (size_t)y * W + x) : 0.f;
     }
     __syncthreads();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[CPT][4];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[k][p] = 0.f;
 #pragma unroll
     for (int eyi = 0; eyi < G; ++eyi) {
-      const float* row = Xs + (cc * HR + r + eyi) * HWD + 4 * qx;
-      const float4 v0 = *reinterpret_cast<const float4*>(row);
-      const float4 v1 = *reinterpret_cast<const float4*>(row + 4);
-      const float4 v2 = *reinterpret_cast<const float4*>(row + 8);
-      const float f[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+      float f[CPT][12];
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const float* row = Xs + ((cg * CPT + k) * HR + r + eyi) * HWD + 4 * qx;
+        const float4 v0 = *reinterpret_cast<const float4*>(row);
+        const float4 v1 = *reinterpret_cast<const float4*>(row + 4);
+        const float4 v2 = *reinterpret_cast<const float4*>(row + 8);
+        f[k][0] = v0.x; f[k][1] = v0.y; f[k][2] = v0.z; f[k][3] = v0.w;
+        f[k][4] = v1.x; f[k][5] = v1.y; f[k][6] = v1.z; f[k][7] = v1.w;
+        f[k][8] = v2.x; f[k][9] = v2.y; f[k][10] = v2.z; f[k][11] = v2.w;
+      }
 #pragma unroll
       for (int exi = 0; exi < G; ++exi) {
         const float4 g4 = *reinterpret_cast<const float4*>(Gt + ((eyi * G + exi) * TH + r) * TW + 4 * qx);
-        acc[0] = fmaf(g4.x, f[0 + exi + (4 - MD)], acc[0]);
-        acc[1] = fmaf(g4.y, f[1 + exi + (4 - MD)], acc[1]);
-        acc[2] = fmaf(g4.z, f[2 + exi + (4 - MD)], acc[2]);
-        acc[3] = fmaf(g4.w, f[3 + exi + (4 - MD)], acc[3]);
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          acc[k][0] = fmaf(g4.x, f[k][0 + exi + (4 - MD)], acc[k][0]);
+          acc[k][1] = fmaf(g4.y, f[k][1 + exi + (4 - MD)], acc[k][1]);
+          acc[k][2] = fmaf(g4.z, f[k][2 + exi + (4 - MD)], acc[k][2]);
+          acc[k][3] = fmaf(g4.w, f[k][3 + exi + (4 - MD)], acc[k][3]);
+        }
       }
     }
-    const int c = c0 + cc, y = y0 + r, xb = x0 + 4 * qx;
-    if (c < C && y < H) {
-      float* o = gX + ((size_t)n * C + c) * plane + (size_t)y * W + xb;
+    const int y = y0 + r, xb = x0 + 4 * qx;
+    if (y < H) {
 #pragma unroll
-      for (int p = 0; p < 4; ++p)
-        if (xb + p < W) o[p] = acc[p] * inv;
+      for (int k = 0; k < CPT; ++k) {
+        const int c = c0 + cg * CPT + k;
+        if (c >= C) continue;
+        float* o = gX + ((size_t)n * C + c) * plane + (size_t)y * W + xb;
+        if (xb + 3 < W && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+          *reinterpret_cast<float4*>(o) = make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (xb + p < W) o[p] = acc[k][p] * inv;
+        }
+      }
     }
   }
 }
