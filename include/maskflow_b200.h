@@ -241,6 +241,23 @@ MFN_API int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, con
                                    float* out, long long out_batch_stride, int N, int Cin, int H, int W, int Cout,
                                    int stride, int dilation, int out_mode, float leaky_slope, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * The step either side of the network.
+ * mfn_preprocess_forward replaces PipelineFlownet.predict / do_batch_mx -- network/pipeline.py:206-212 (`/ 255.0`),
+ *   :85-87 (centralize: subtract the per-sample RGB mean taken over BOTH images), :122-130 (BilinearResize2D to the next
+ *   multiple of 64, or to `resize`).  img1 / img2: (N,C,H,W) uint8 (is_uint8 = 1, values / 255) or float32 already in
+ *   [0,1]; out1 / out2: (N,C,OH,OW) float32; rgb_mean: (N*C) float32 (the subtracted means).  OH == H and OW == W skips
+ *   the resampling, like the reference.
+ * mfn_postprocess_forward replaces do_batch / predict -- network/pipeline.py:137-141 (Upsample(4) of the finest
+ *   prediction, BilinearResize2D back to the input size times (H/H', W/W') per flow channel) and :217-218 (NCHW -> NHWC,
+ *   flip (y,x) -> (x,y)): pred (N,channels,Hq,Wq) -> out (N,H,W,channels), channels reversed when flip_channels;
+ *   is_flow = 1 applies the per-channel rescale (channel 0 = y).  is_flow = 0 serves the occlusion mask (:138,142).
+ * ------------------------------------------------------------------------------------------------- */
+MFN_API int mfn_preprocess_forward(const void* img1, const void* img2, int is_uint8, float* out1, float* out2,
+                                   float* rgb_mean, int N, int C, int H, int W, int OH, int OW, void* stream);
+MFN_API int mfn_postprocess_forward(const float* pred, float* out, int N, int channels, int Hq, int Wq, int H, int W,
+                                    int flip_channels, int is_flow, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

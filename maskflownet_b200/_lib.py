@@ -33,6 +33,8 @@ SIGNATURES = {
     "mfn_grid_generator_warp_forward": [_f, _f, _i, _i, _i, _f],
     "mfn_bilinear_sampler_forward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "mfn_image_warp_concat_forward": [_f] * 6 + [_i] * 4 + [_fl, _f],
+    "mfn_preprocess_forward": [_f, _f, _i, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
+    "mfn_postprocess_forward": [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _f],
     "mfn_set_tuning": [ctypes.c_char_p, _i],
     "mfn_conv3x3_pack_weights": [_f, _f, _i, _i, _f],
     "mfn_conv3x3_forward": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _fl, _f],

@@ -381,6 +381,21 @@ def predict_flow(net: nn.Module, img1_u8: torch.Tensor, img2_u8: torch.Tensor) -
     return ops.upsample(preds[-1], 4)
 
 
+@torch.no_grad()
+def predict(net: nn.Module, img1: torch.Tensor, img2: torch.Tensor, resize=None):
+    """PipelineFlownet.predict for one batch (network/pipeline.py:189-223), fused: uint8 (or [0,1] float) pairs (N,3,H,W) of
+    ANY size -> /255 + centralize + BilinearResize2D to multiples of 64 (one op) -> network -> Upsample(4) + resize back +
+    per-channel rescale + NHWC + (y,x)->(x,y) flip (one op).  Returns (flow (N,H,W,2) in (x,y) pixels -- the .flo layout,
+    occlusion mask (N,H,W,1))."""
+    N, _, H, W = img1.shape
+    a, b, _ = ops.preprocess(img1, img2, ops.padded_size(H, W, resize))
+    preds, occ, _ = net(a, b)
+    flow = ops.postprocess(preds[-1], H, W, flip_channels=True, is_flow=True)
+    mask = ops.postprocess(occ[0], H, W, flip_channels=False, is_flow=False) if occ and occ[0].shape[1] == 1 and \
+        occ[0].shape[2] * 4 == a.shape[2] else None
+    return flow, mask
+
+
 class FlowPredictor:
     """predict_flow captured in a CUDA graph: one graph per input shape, static uint8 input buffers, one cudaGraphLaunch
     per call (the eager step is ~115 dependent launches; the graph removes the launch gaps between them).

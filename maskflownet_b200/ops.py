@@ -460,3 +460,44 @@ def conv3x3(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor],
                       dtype=torch.float32)
     conv3x3_slices(x, 0, x.shape[1], packed, bias, out, 0, Cout, leaky_slope, dilation, stride)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Pre / post-processing around the network (row N3)
+# ----------------------------------------------------------------------------------------------------------
+def padded_size(H: int, W: int, resize=None):
+    """Network input size for an (H, W) image: the next multiples of 64 (network/pipeline.py:122-124), or `resize`."""
+    if resize is not None:
+        return int(resize[0]), int(resize[1])
+    return H + (64 - H % 64) % 64, W + (64 - W % 64) % 64
+
+
+def preprocess(img1: torch.Tensor, img2: torch.Tensor, out_hw=None):
+    """/255 (uint8 input) -> centralize -> BilinearResize2D to out_hw: what PipelineFlownet.predict + do_batch_mx do before
+    the network (network/pipeline.py:206-212, 85-87, 117-130).  Returns (im1, im2, rgb_mean (N,C,1,1)).  Forward only."""
+    for t, nm in ((img1, "img1"), (img2, "img2")):
+        if not (t.is_cuda and t.is_contiguous() and t.dim() == 4 and t.dtype in (torch.uint8, torch.float32)):
+            raise MaskflowError(f"preprocess: {nm} must be a contiguous CUDA uint8 / float32 NCHW tensor")
+    if img1.shape != img2.shape or img1.dtype != img2.dtype:
+        raise MaskflowError("preprocess: img1 and img2 must agree in shape and dtype")
+    _no_grad_path("preprocess", img1, img2)
+    N, C, H, W = img1.shape
+    OH, OW = (H, W) if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
+    o1 = torch.empty((N, C, OH, OW), device=img1.device, dtype=torch.float32)
+    o2 = torch.empty_like(o1)
+    mean = torch.empty((N, C, 1, 1), device=img1.device, dtype=torch.float32)
+    _call("mfn_preprocess_forward", img1.device, _p(img1), _p(img2), 1 if img1.dtype == torch.uint8 else 0, _p(o1), _p(o2),
+          _p(mean), N, C, H, W, OH, OW)
+    return o1, o2, mean
+
+
+def postprocess(pred: torch.Tensor, H: int, W: int, flip_channels: bool = True, is_flow: bool = True) -> torch.Tensor:
+    """Upsample(4) -> BilinearResize2D back to (H, W) (flow rescaled per channel) -> NHWC -> (y,x) to (x,y) flip: what
+    do_batch + predict do after the network (network/pipeline.py:137-141, 217-218).  pred (N,ch,Hq,Wq) -> (N,H,W,ch)."""
+    p = _chk(pred, "postprocess.pred")
+    _no_grad_path("postprocess", p)
+    N, CH, Hq, Wq = p.shape
+    out = torch.empty((N, H, W, CH), device=p.device, dtype=torch.float32)
+    _call("mfn_postprocess_forward", p.device, _p(p), _p(out), N, CH, Hq, Wq, int(H), int(W), 1 if flip_channels else 0,
+          1 if is_flow else 0)
+    return out

@@ -195,3 +195,22 @@ def test_flow_predictor_cuda_graph_equals_eager():
         got = pred(a, b).clone()
         assert torch.equal(ref, got)
 
+
+
+def test_predict_any_size_matches_oracle_pipeline():
+    """network.predict (PipelineFlownet.predict: resize to x64, forward, Upsample(4), resize back, flip) on a 50x100 pair
+    against the oracle network + oracle pre/post-processing."""
+    from oracle import prepost_ref
+    model = _named_model()
+    rng = np.random.default_rng(3)
+    u1 = rng.integers(0, 256, (1, 3, 50, 100), dtype=np.uint8)
+    u2 = rng.integers(0, 256, (1, 3, 50, 100), dtype=np.uint8)
+    flow, occ = network.predict(model, torch.from_numpy(u1).cuda(), torch.from_numpy(u2).cuda())
+    assert flow.shape == (1, 50, 100, 2) and occ.shape == (1, 50, 100, 1)
+    a, b, _ = prepost_ref.preprocess(u1, u2, prepost_ref.padded_size(50, 100))
+    params = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    with torch.no_grad():
+        preds, o, _ = network_ref.maskflownet_s_forward(params, torch.from_numpy(a), torch.from_numpy(b), threads=8)
+    ref = prepost_ref.postprocess(preds[-1].numpy(), 50, 100)
+    assert np.abs(flow.cpu().numpy() - ref).max() < 5e-3
+    assert np.abs(occ.cpu().numpy() - prepost_ref.postprocess(o[0].numpy(), 50, 100, False, False)).max() < 1e-3

@@ -601,3 +601,33 @@ def test_warp_mask_tensor_core_forward(N, C, F, H, W, border):
                                     packed_weight=ops.conv3x3_pack(cu(w)))
     assert m2 is None
     assert np.abs(out2.cpu().numpy() - ref2.numpy()).max() <= 1e-4 * max(1.0, float(ref2.abs().max()))
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+@pytest.mark.parametrize("shape,resize", [((2, 3, 20, 30), None), ((1, 3, 64, 128), None), ((1, 3, 436, 1024), (448, 1024)),
+                                          ((2, 3, 37, 50), (64, 128))])
+def test_preprocess_postprocess_match_oracle(shape, resize, dtype):
+    """Row N3: fused /255 + centralize + BilinearResize2D, and Upsample(4) + resize-back + rescale + NHWC + flip, against
+    the numpy restatement (oracle/prepost_ref.py) of network/pipeline.py:85-87,117-147,206-221."""
+    from oracle import prepost_ref
+    rng = np.random.default_rng(8)
+    N, C, H, W = shape
+    if dtype == "u8":
+        i1 = rng.integers(0, 256, shape, dtype=np.uint8)
+        i2 = rng.integers(0, 256, shape, dtype=np.uint8)
+    else:
+        i1, i2 = rng.random(shape).astype(np.float32), rng.random(shape).astype(np.float32)
+    hw = prepost_ref.padded_size(H, W, resize)
+    assert ops.padded_size(H, W, resize) == hw
+    ra, rb, rm = prepost_ref.preprocess(i1, i2, hw)
+    a, b, m = ops.preprocess(torch.from_numpy(i1).to(DEV), torch.from_numpy(i2).to(DEV), hw)
+    assert np.abs(m.cpu().numpy() - rm).max() <= 2e-6
+    assert np.abs(a.cpu().numpy() - ra).max() <= 1e-5 and np.abs(b.cpu().numpy() - rb).max() <= 1e-5
+    pred = (rng.standard_normal((N, 2, hw[0] // 4, hw[1] // 4)) * 5).astype(np.float32)
+    got = ops.postprocess(cu(pred), H, W).cpu().numpy()
+    ref = prepost_ref.postprocess(pred, H, W)
+    assert got.shape == (N, H, W, 2)
+    assert np.abs(got - ref).max() <= 1e-4
+    occ = rng.random((N, 1, hw[0] // 4, hw[1] // 4)).astype(np.float32)
+    got = ops.postprocess(cu(occ), H, W, flip_channels=False, is_flow=False).cpu().numpy()
+    assert np.abs(got - prepost_ref.postprocess(occ, H, W, False, False)).max() <= 1e-5

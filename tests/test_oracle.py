@@ -117,3 +117,32 @@ def test_warp_mask_composition_matches_c_oracle():
     offs = np.repeat((fu_c * 20.0 / 8)[:, None], 9, 1).reshape(N, 18, H, W)
     pre = cref.deformable_conv_forward(x, offs, w, b) * (1 / (1 + np.exp(-mu_c))) + tr
     assert np.abs(np.where(pre > 0, pre, 0.1 * pre) - out.numpy()).max() < 2e-5
+
+
+def test_prepost_oracle_against_torch_interpolate_and_roundtrip(tmp_path):
+    """BilinearResize2D restatement == torch F.interpolate(align_corners=True); centralize; .flo / KITTI encoders round-trip."""
+    from oracle import prepost_ref
+    from maskflownet_b200 import flowio
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((2, 3, 13, 21)).astype(np.float32)
+    for oh, ow in ((64, 64), (13, 21), (7, 40), (26, 11)):
+        ref = torch.nn.functional.interpolate(torch.from_numpy(x), size=(oh, ow), mode="bilinear", align_corners=True).numpy()
+        assert np.abs(prepost_ref.bilinear_resize2d(x, oh, ow) - ref).max() < 2e-5
+    u1 = rng.integers(0, 256, (2, 3, 20, 30), dtype=np.uint8)
+    u2 = rng.integers(0, 256, (2, 3, 20, 30), dtype=np.uint8)
+    a, b, m = prepost_ref.preprocess(u1, u2, prepost_ref.padded_size(20, 30))
+    assert a.shape == (2, 3, 64, 64)
+    assert np.abs(np.concatenate([u1, u2], 2).astype(np.float64).mean((2, 3)) / 255 - m[:, :, 0, 0]).max() < 1e-6
+    a0, b0, _ = prepost_ref.preprocess(u1, u2, None)
+    assert abs(float(np.concatenate([a0, b0], 2).mean())) < 1e-6          # centralised
+    pred = rng.standard_normal((1, 2, 16, 16)).astype(np.float32)
+    out = prepost_ref.postprocess(pred, 64, 64)                            # no resize: Upsample(4), NHWC, flip
+    up = cref.upsample(pred, 4)
+    assert np.array_equal(out[0, :, :, 0], up[0, 1]) and np.array_equal(out[0, :, :, 1], up[0, 0])
+    out2 = prepost_ref.postprocess(pred, 50, 60)
+    assert out2.shape == (1, 50, 60, 2)
+    flowio.write_flo(str(tmp_path / "a.flo"), out2[0])
+    assert np.array_equal(flowio.read_flo(str(tmp_path / "a.flo")), out2[0])
+    k = flowio.encode_kitti(out2[0])
+    f, valid = flowio.decode_kitti(k)
+    assert valid.all() and np.abs(f - out2[0]).max() <= 1 / 128 + 1e-6
