@@ -53,6 +53,11 @@ __host__ __device__ inline int tap_xoff(int kx, int stride, int dil) {
 __host__ __device__ inline int row_of_slot(int slot, int y0, int stride, int dil) {
   return stride == 2 ? 2 * y0 - 1 + slot : (dil >= R ? y0 + (slot % R) + (slot / R - 1) * dil : y0 - dil + slot);
 }
+// ext = 2 ("band" mode of K3 through linearity, warp_lin.cu): the input is a VIRTUAL image of (n + 6) rows / columns --
+// the n real ones followed by [0, 0, first, 0, 0, last] -- so that ONE convolution also yields the 1-D convolutions of the
+// first / last row and column and the four corner pixels that the MXNet-1.5 border rule needs.  Maps a virtual
+// coordinate to the real one, or -1 (zero).
+__host__ __device__ inline int band_map(int v, int n) { return v < n ? v : (v == n + 2 ? 0 : (v == n + 5 ? n - 1 : -1)); }
 __host__ __device__ inline int x_of_entry(int p, int x0, int stride, int dil) {
   return stride == 2 ? (p < MT ? 2 * (x0 + p) : 2 * (x0 - 1 + p - MT) + 1) : x0 - dil + p;
 }
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
       // ext = 1: "full" convolution -- the output grid is the input grid extended by one pixel on every side
       // (OH = H + 2, OW = W + 2; output (y, x) sits at input position (y - 1, x - 1)); used by K3 through linearity
-      const int x0 = tx * MT - ext, y0 = ty * R - ext;
+      const int x0 = tx * MT - (ext ? 1 : 0), y0 = ty * R - (ext ? 1 : 0);
       const float* xn = x + (size_t)n * x_bs;
       // The producers are bound by their own instruction stream (ncu: ~150 integer instructions per item for the tile
       // geometry), so when a chunk is one batch per warp (the common 2-row, dilation-1 tile) the per-item geometry -- source
@@ -384,7 +389,11 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
           const int t = pw + b * NPROD;
           const int kc = t & 1, e = (t >> 1) * 32 + lane;
           const int slot = e / PW, pe = e - slot * PW;
-          const int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(pe, x0, stride, dil);
+          int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(pe, x0, stride, dil);
+          if (ext == 2) {
+            y = y >= 0 ? band_map(y, H) : -1;
+            xx = xx >= 0 ? band_map(xx, W) : -1;
+          }
           const bool act = t < nItems && e < E;
           const bool ok = act && y >= 0 && y < H && xx >= 0 && xx < W;
           goff[b] = ok ? y * W + xx : -1;
@@ -464,7 +473,11 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
             const int t = k0 + b * NPROD;
             const int kc = t & 1, e = (t >> 1) * 32 + lane;
             const int slot = e / PW, p = e - slot * PW;
-            const int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(p, x0, stride, dil);
+            int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(p, x0, stride, dil);
+            if (ext == 2) {
+              y = y >= 0 ? band_map(y, H) : -1;
+              xx = xx >= 0 ? band_map(xx, W) : -1;
+            }
             const bool ok = t < nItems && e < E && y >= 0 && y < H && xx >= 0 && xx < W;
             const int c0 = 16 * c + 8 * kc;
             const float* src = xn + (size_t)c0 * plane + (size_t)(ok ? y : 0) * W + (ok ? xx : 0);
@@ -523,12 +536,13 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
                         float slope, cudaStream_t st, int ext) {
   using namespace um;
   if (Cout > 256 || (stride != 1 && !(stride == 2 && dil == 1))) return -1;
-  if (ext != 0 && !(ext == 1 && stride == 1 && dil == 1 && out_mode == 0)) return -1;
+  if (ext != 0 && !((ext == 1 || ext == 2) && stride == 1 && dil == 1 && out_mode == 0)) return -1;
   const int CoutP = um::cout_pad(Cout), nChunks = (Cin + 15) / 16;
   const int E = n_slots(stride, dil) * row_pitch(stride, dil);
   const SmemMap sm = smem_map(E, CoutP);
   if (sm.WS < 2 || E * 16 > 0x3FFF * 16) return -1;
-  const int OH = stride == 2 ? (H - 1) / 2 + 1 : H + 2 * ext, OW = stride == 2 ? (W - 1) / 2 + 1 : W + 2 * ext;
+  const int grow = ext == 2 ? 8 : 2 * ext;   // ext 1: grid + 1 pixel per side; ext 2: + the six band rows / columns too
+  const int OH = stride == 2 ? (H - 1) / 2 + 1 : H + grow, OW = stride == 2 ? (W - 1) / 2 + 1 : W + grow;
   static SmemOptIn opt0, opt3, opt9;
   {
     cudaError_t e = ensure_dyn_smem(conv3x3_umma_kernel<false, 1>, sm.total, opt0);

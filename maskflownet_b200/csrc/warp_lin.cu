@@ -16,8 +16,10 @@
 //   D x Z : sum_i alpha_i * lerp_w( Rrow[B_i][i] )   with Rrow[B][i] = conv1d(x[row B], W[i, :]) on the extended row,
 //   Z x D : sum_j beta_j  * lerp_h( Rcol[B_j][j] )   with Rcol[B][j] = conv1d(x[:, col B], W[:, j]),
 //   D x D : sum_ij alpha_i beta_j T[B_i][B_j][i][j]  with T = W_ij . x[:, row B_i, col B_j]
-// (B = first / last row or column).  The three tables are tiny (one launch); only pixels whose taps reach the one-pixel bands
-// read them.  Band membership uses the same float expression (y - 1 + i) + dy as the reference kernel, so the operator's
+// (B = first / last row or column).  The three tables come out of the SAME tensor-core convolution: in its ext = 2 mode
+// the kernel reads a virtual image whose rows / columns n .. n+5 are [0, 0, first, 0, 0, last], so the isolated copies of
+// the border rows / columns / corner pixels produce exactly Rrow, Rcol and T next to Yext (one launch, ~10-40 % more
+// tiles).  Only pixels whose taps reach the one-pixel bands read them.  Band membership uses the same float expression (y - 1 + i) + dy as the reference kernel, so the operator's
 // discontinuities (h = 0, h = H) are taken on the same side as the tap-by-tap kernels and the oracle.
 #include "mma_tiles.cuh"
 
@@ -50,86 +52,36 @@ __device__ __forceinline__ Band bands(int p, float d, int n) {
   return b;
 }
 
-// linear interpolation of a zero-extended table row t[0 .. n+1] (entry v <-> position v - 1) at position q
-__device__ __forceinline__ float lerp_ext(const float* __restrict__ t, int n, float q) {
+// linear interpolation along one axis of a zero-extended table t[0 .. n+1] (entry v <-> position v - 1, element stride
+// `st`) at position q
+__device__ __forceinline__ float lerp_ext(const float* __restrict__ t, int n, float q, int st) {
   const float fl = floorf(q);
   const int i0 = (int)fl + 1;
   const float l = q - fl;
   float v = 0.f;
-  if (i0 >= 0 && i0 <= n + 1) v += (1.f - l) * __ldg(t + i0);
-  if (i0 + 1 >= 0 && i0 + 1 <= n + 1) v += l * __ldg(t + i0 + 1);
+  if (i0 >= 0 && i0 <= n + 1) v += (1.f - l) * __ldg(t + (size_t)i0 * st);
+  if (i0 + 1 >= 0 && i0 + 1 <= n + 1) v += l * __ldg(t + (size_t)(i0 + 1) * st);
   return v;
 }
 
-// Rrow[n][B][i][f][W+2], Rcol[n][B][j][f][H+2], T[n][Br][Bc][i][j][f]
-__global__ void __launch_bounds__(256)
-    warp_tables_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ Rrow,
-                       float* __restrict__ Rcol, float* __restrict__ T, int N, int C, int H, int W, int F) {
-  const long long nRow = (long long)N * 6 * F * (W + 2), nCol = (long long)N * 6 * F * (H + 2), nT = (long long)N * 36 * F;
-  const size_t plane = (size_t)H * W;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nRow + nCol + nT;
-       idx += (long long)gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    if (idx < nRow) {
-      const int v = (int)(idx % (W + 2));
-      const int f = (int)((idx / (W + 2)) % F);
-      const int i = (int)((idx / ((long long)(W + 2) * F)) % 3);
-      const int B = (int)((idx / ((long long)(W + 2) * F * 3)) % 2);
-      const int n = (int)(idx / ((long long)(W + 2) * F * 6));
-      const float* xr = x + (size_t)n * C * plane + (size_t)(B ? H - 1 : 0) * W;
-      const float* wf = w + (size_t)f * C * 9 + 3 * i;
-      for (int c = 0; c < C; ++c) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int xx = v - 1 + j - 1;
-          if (xx >= 0 && xx < W) acc = fmaf(__ldg(wf + (size_t)c * 9 + j), __ldg(xr + (size_t)c * plane + xx), acc);
-        }
-      }
-      Rrow[idx] = acc;
-    } else if (idx < nRow + nCol) {
-      const long long k = idx - nRow;
-      const int u = (int)(k % (H + 2));
-      const int f = (int)((k / (H + 2)) % F);
-      const int j = (int)((k / ((long long)(H + 2) * F)) % 3);
-      const int B = (int)((k / ((long long)(H + 2) * F * 3)) % 2);
-      const int n = (int)(k / ((long long)(H + 2) * F * 6));
-      const float* xc = x + (size_t)n * C * plane + (B ? W - 1 : 0);
-      const float* wf = w + (size_t)f * C * 9 + j;
-      for (int c = 0; c < C; ++c) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int yy = u - 1 + i - 1;
-          if (yy >= 0 && yy < H) acc = fmaf(__ldg(wf + (size_t)c * 9 + 3 * i), __ldg(xc + (size_t)c * plane + (size_t)yy * W), acc);
-        }
-      }
-      Rcol[k] = acc;
-    } else {
-      const long long k = idx - nRow - nCol;
-      const int f = (int)(k % F);
-      const int ij = (int)((k / F) % 9);
-      const int Bc = (int)((k / ((long long)F * 9)) % 2);
-      const int Br = (int)((k / ((long long)F * 18)) % 2);
-      const int n = (int)(k / ((long long)F * 36));
-      const float* xp = x + (size_t)n * C * plane + (size_t)(Br ? H - 1 : 0) * W + (Bc ? W - 1 : 0);
-      const float* wf = w + (size_t)f * C * 9 + ij;
-      for (int c = 0; c < C; ++c) acc = fmaf(__ldg(wf + (size_t)c * 9), __ldg(xp + (size_t)c * plane), acc);
-      T[k] = acc;
-    }
-  }
-}
-
-// One thread per pixel, loop over the F output channels (all accesses coalesced along x).
+// Yall = conv3x3_umma(ext = 2): (N, F, H + 8, W + 8); entry (r, v) <-> position (r - 1, v - 1) of the virtual image
+//   rows 0 .. H+1, cols 0 .. W+1   Yext (the extended convolution)
+//   rows H+4-i / H+7-i             the 1-D convolution of the first / last image row with weight row i   (Rrow)
+//   cols W+4-j / W+7-j             ... of the first / last image column with weight column j               (Rcol)
+//   their intersections            W_ij . x[corner]                                                         (T)
+// One thread per (pixel, chunk of FCH output channels): all accesses coalesced along x.
+constexpr int FCH = 16;
 template <int BORDER>
 __global__ void __launch_bounds__(256)
-    warp_lin_kernel(const float* __restrict__ Yext, const float* __restrict__ Rrow, const float* __restrict__ Rcol,
-                    const float* __restrict__ T, const float* __restrict__ flow_c, const float* __restrict__ mask_c,
+    warp_lin_kernel(const float* __restrict__ Yall, const float* __restrict__ flow_c, const float* __restrict__ mask_c,
                     const float* __restrict__ bias, const float* __restrict__ tradeoff, float* __restrict__ out,
                     float* __restrict__ flow_up_out, float* __restrict__ mask_up_out, int N, int H, int W, int F, int up,
-                    float flow_scale, float level_stride, float slope) {
+                    float flow_scale, float level_stride, float slope, int grow) {
   const long long total = (long long)N * H * W;
   const size_t plane = (size_t)H * W;
-  const int WE = W + 2, HE = H + 2;
-  const size_t eplane = (size_t)HE * WE;
+  const int WA = W + grow, HA = H + grow;
+  const size_t aplane = (size_t)HA * WA;
+  const int f0 = blockIdx.y * FCH, f1 = min(F, f0 + FCH);
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     const int xq = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / plane);
     const int Hc = H / up, Wc = W / up;
@@ -138,19 +90,20 @@ __global__ void __launch_bounds__(256)
     const float fx = upsample_at(fc + (size_t)Hc * Wc, Hc, Wc, up, y, xq);
     const float mask_v = mask_c ? upsample_at(mask_c + (size_t)n * Hc * Wc, Hc, Wc, up, y, xq) : 0.f;
     const size_t pix = (size_t)y * W + xq;
-    if (flow_up_out) {
-      flow_up_out[((size_t)n * 2 + 0) * plane + pix] = fy;
-      flow_up_out[((size_t)n * 2 + 1) * plane + pix] = fx;
+    if (blockIdx.y == 0) {
+      if (flow_up_out) {
+        flow_up_out[((size_t)n * 2 + 0) * plane + pix] = fy;
+        flow_up_out[((size_t)n * 2 + 1) * plane + pix] = fx;
+      }
+      if (mask_up_out && mask_c) mask_up_out[(size_t)n * plane + pix] = mask_v;
     }
-    if (mask_up_out && mask_c) mask_up_out[(size_t)n * plane + pix] = mask_v;
     // offsets exactly as the reference rounds them: (flow * scale) / stride   (MaskFlownet.py:230)
     const float dy = __fdiv_rn(__fmul_rn(fy, flow_scale), level_stride);
     const float dx = __fdiv_rn(__fmul_rn(fx, flow_scale), level_stride);
     const float h0 = (float)y + dy, w0 = (float)xq + dx;
-    // ---- Z x Z: bilinear sample of the extended convolution (entry (u, v) <-> position (u - 1, v - 1)) ----
+    // ---- Z x Z: bilinear sample of the extended convolution ----
     const float fh = floorf(h0), fw = floorf(w0);
-    // far outside: keep the integer conversion defined
-    const bool farout = !(h0 > -3.f && h0 < (float)(H + 2) && w0 > -3.f && w0 < (float)(W + 2));
+    const bool farout = !(h0 > -3.f && h0 < (float)(H + 2) && w0 > -3.f && w0 < (float)(W + 2));   // keeps the int conversion defined
     const int i0 = farout ? -8 : (int)fh + 1, j0 = farout ? -8 : (int)fw + 1;
     const float lh = h0 - fh, lw = w0 - fw;
     const bool r0 = i0 >= 0 && i0 <= H + 1, r1 = i0 + 1 >= 0 && i0 + 1 <= H + 1;
@@ -159,7 +112,7 @@ __global__ void __launch_bounds__(256)
     const float w10 = (r1 && c0) ? lh * (1.f - lw) : 0.f, w11 = (r1 && c1) ? lh * lw : 0.f;
     const int ic0 = min(max(i0, 0), H + 1), ic1 = min(max(i0 + 1, 0), H + 1);
     const int jc0 = min(max(j0, 0), W + 1), jc1 = min(max(j0 + 1, 0), W + 1);
-    const int o00 = ic0 * WE + jc0, o01 = ic0 * WE + jc1, o10 = ic1 * WE + jc0, o11 = ic1 * WE + jc1;
+    const int o00 = ic0 * WA + jc0, o01 = ic0 * WA + jc1, o10 = ic1 * WA + jc0, o11 = ic1 * WA + jc1;
     const bool anyz = (w00 != 0.f) || (w01 != 0.f) || (w10 != 0.f) || (w11 != 0.f);
     Band bh, bw;
     bh.any = bw.any = false;
@@ -168,79 +121,67 @@ __global__ void __launch_bounds__(256)
       bw = bands(xq, dx, W);
     }
     const float sig = mask_c ? sigmoidf_(mask_v) : 1.f;
-    const float* yp = Yext + (size_t)n * F * eplane;
-    float* op = out + (size_t)n * F * plane + pix;
-    const float* tp = tradeoff ? tradeoff + (size_t)n * F * plane + pix : nullptr;
-    const float* rrow = Rrow + (size_t)n * 6 * F * WE;
-    const float* rcol = Rcol + (size_t)n * 6 * F * HE;
-    const float* tt = T + (size_t)n * 36 * F;
+    const float* yp = Yall + ((size_t)n * F + f0) * aplane;
+    float* op = out + ((size_t)n * F + f0) * plane + pix;
+    const float* tp = tradeoff ? tradeoff + ((size_t)n * F + f0) * plane + pix : nullptr;
 #pragma unroll 4
-    for (int f = 0; f < F; ++f) {
-      const float* q = yp + (size_t)f * eplane;
+    for (int f = f0; f < f1; ++f, yp += aplane, op += plane) {
       float v = 0.f;
-      if (anyz) v = w00 * __ldg(q + o00) + w01 * __ldg(q + o01) + w10 * __ldg(q + o10) + w11 * __ldg(q + o11);
+      if (anyz) v = w00 * __ldg(yp + o00) + w01 * __ldg(yp + o01) + w10 * __ldg(yp + o10) + w11 * __ldg(yp + o11);
       if (BORDER == MFN_BORDER_MXNET15 && (bh.any || bw.any)) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-          if (bh.a[i] != 0.f) v += bh.a[i] * lerp_ext(rrow + ((size_t)(bh.B[i] * 3 + i) * F + f) * WE, W, w0);
+        for (int i = 0; i < 3; ++i)    // tap row i in a band: + a_i * lerp_w of the band row's 1-D convolution
+          if (bh.a[i] != 0.f) v += bh.a[i] * lerp_ext(yp + (size_t)(H + 4 + 3 * bh.B[i] - i) * WA, W, w0, 1);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-          if (bw.a[j] != 0.f) v += bw.a[j] * lerp_ext(rcol + ((size_t)(bw.B[j] * 3 + j) * F + f) * HE, H, h0);
+          if (bw.a[j] != 0.f) v += bw.a[j] * lerp_ext(yp + (W + 4 + 3 * bw.B[j] - j), H, h0, WA);
         if (bh.any && bw.any) {
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j)
               if (bh.a[i] != 0.f && bw.a[j] != 0.f)
-                v += bh.a[i] * bw.a[j] * __ldg(tt + ((size_t)((bh.B[i] * 2 + bw.B[j]) * 9 + 3 * i + j)) * F + f);
+                v += bh.a[i] * bw.a[j] * __ldg(yp + (size_t)(H + 4 + 3 * bh.B[i] - i) * WA + (W + 4 + 3 * bw.B[j] - j));
         }
       }
       if (bias) v += __ldg(bias + f);
       v *= sig;
-      if (tp) v += __ldg(tp + (size_t)f * plane);
-      op[(size_t)f * plane] = leaky(v, slope);
+      if (tp) {
+        v += __ldg(tp);
+        tp += plane;
+      }
+      *op = leaky(v, slope);
     }
   }
 }
 
 }  // namespace wl
 
-long long warp_lin_workspace_bytes(int N, int F, int H, int W) {
-  const long long ye = (long long)N * F * (H + 2) * (W + 2), tr = (long long)N * 6 * F * (W + 2), tc = (long long)N * 6 * F * (H + 2),
-                  t = (long long)N * 36 * F;
-  return (ye + tr + tc + t) * 4 + 64;
-}
+long long warp_lin_workspace_bytes(int N, int F, int H, int W) { return (long long)N * F * (H + 8) * (W + 8) * 4 + 64; }
 
 // returns -1 when the extended tcgen05 convolution does not fit the shape (caller uses the list-based path)
 int launch_warp_lin(const float* x, const float* flow_c, const float* mask_c, const float* weight, const void* packed_weight,
                     const float* bias, const float* tradeoff, void* workspace, float* out, float* fup, float* mup, int N,
                     int C, int H, int W, int F, int up, float fs, float ls, float slope, int border_mode, cudaStream_t st) {
   using namespace wl;
-  float* Yext = static_cast<float*>(workspace);
-  float* Rrow = Yext + (size_t)N * F * (H + 2) * (W + 2);
-  float* Rcol = Rrow + (size_t)N * 6 * F * (W + 2);
-  float* T = Rcol + (size_t)N * 6 * F * (H + 2);
+  (void)weight;
+  float* Yall = static_cast<float*>(workspace);
   const unsigned char* wp = static_cast<const unsigned char*>(packed_weight);
-  int rc = conv3x3_umma_launch(x, (long long)C * H * W, wp + conv3x3_sync_packed_bytes(C, F), nullptr, Yext,
-                               (long long)F * (H + 2) * (W + 2), N, C, H, W, F, 1, 1, MFN_CONV_OUT_NCHW, 1.0f, st, 1);
+  // zero-corner rule: the extended convolution alone (grid + 1 pixel per side); MXNet-1.5 rule: + the band rows / columns
+  const int ext = border_mode == MFN_BORDER_MXNET15 ? 2 : 1, grow = ext == 2 ? 8 : 2;
+  int rc = conv3x3_umma_launch(x, (long long)C * H * W, wp + conv3x3_sync_packed_bytes(C, F), nullptr, Yall,
+                               (long long)F * (H + grow) * (W + grow), N, C, H, W, F, 1, 1, MFN_CONV_OUT_NCHW, 1.0f, st, ext);
   if (rc) return rc;
-  if (border_mode == MFN_BORDER_MXNET15) {
-    const long long tot = (long long)N * 6 * F * (W + 2) + (long long)N * 6 * F * (H + 2) + (long long)N * 36 * F;
-    long long blocks = (tot + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
-    warp_tables_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, weight, Rrow, Rcol, T, N, C, H, W, F);
-    rc = check_launch("warp_tables_kernel");
-    if (rc) return rc;
-  }
   const long long total = (long long)N * H * W;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  const dim3 grid((unsigned)blocks, (unsigned)((F + FCH - 1) / FCH));
   if (border_mode == MFN_BORDER_MXNET15)
-    warp_lin_kernel<MFN_BORDER_MXNET15><<<(unsigned)blocks, 256, 0, st>>>(Yext, Rrow, Rcol, T, flow_c, mask_c, bias, tradeoff, out,
-                                                                         fup, mup, N, H, W, F, up, fs, ls, slope);
+    warp_lin_kernel<MFN_BORDER_MXNET15><<<grid, 256, 0, st>>>(Yall, flow_c, mask_c, bias, tradeoff, out, fup, mup, N, H, W, F, up,
+                                                             fs, ls, slope, grow);
   else
-    warp_lin_kernel<MFN_BORDER_ZERO_CORNER><<<(unsigned)blocks, 256, 0, st>>>(Yext, Rrow, Rcol, T, flow_c, mask_c, bias, tradeoff,
-                                                                             out, fup, mup, N, H, W, F, up, fs, ls, slope);
+    warp_lin_kernel<MFN_BORDER_ZERO_CORNER><<<grid, 256, 0, st>>>(Yall, flow_c, mask_c, bias, tradeoff, out, fup, mup, N, H, W, F,
+                                                                 up, fs, ls, slope, grow);
   return check_launch("warp_lin_kernel");
 }
 

@@ -60,8 +60,9 @@ def main():
         N, C, H, W = shape
         D = (2 * md + 1) ** 2
         out = torch.empty(N, D, H, W, device=dev)
-        for tma in (1, 0):
+        for tma, rbk in ((1, 1), (2, 1), (0, 0)):     # compact step loop / fully unrolled / round-1 ring kernel
             _lib.set_tuning("corr_tma", tma)
+            _lib.set_tuning("corr_rb", rbk)
             fn = lambda: ops.correlation(f1, f2, pad_size=md, max_displacement=md, leaky_slope=0.1,  # noqa: E731
                                          algo=ops.CORR_MMA_BF16X3, out=out)
             for _ in range(3):
@@ -83,6 +84,7 @@ def main():
                               "us_min": round(min(ts) * 1e3, 2), "gbs": round(nbytes / avg / 1e6, 1),
                               "frac_6572": round(nbytes / avg / 1e6 / 6572.2, 4)}), flush=True)
         _lib.set_tuning("corr_tma", 1)
+        _lib.set_tuning("corr_rb", 1)
     return 0
 
 
