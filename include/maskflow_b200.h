@@ -237,6 +237,9 @@ MFN_API int mfn_conv3x3_forward(const float* x, long long x_batch_stride, const 
                                 float leaky_slope, void* stream);
 #define MFN_CONV_OUT_NCHW 0
 #define MFN_CONV_OUT_DEPTH_TO_SPACE2 1
+/* out_mode | (k << 8), NCHW only: the first k output channels are written without the activation (a linear head that shares
+ * the input pass of an activated layer; network.py folds pred_flow / pred_mask over the dense block's input into conv{L}_4) */
+#define MFN_CONV_OUT_LINEAR_PREFIX(k) ((k) << 8)
 MFN_API int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, const void* packed_weight, const float* bias,
                                    float* out, long long out_batch_stride, int N, int Cin, int H, int W, int Cout,
                                    int stride, int dilation, int out_mode, float leaky_slope, void* stream);

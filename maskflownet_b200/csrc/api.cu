@@ -51,6 +51,8 @@ extern "C" int mfn_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "warp_lin")) mfn::tuning().warp_lin = value;
   else if (!strcmp(key, "corr_rb")) mfn::tuning().corr_rb = value;
   else if (!strcmp(key, "corr_tma")) mfn::tuning().corr_tma = value;
+  else if (!strcmp(key, "corr_ts_lo")) mfn::tuning().corr_ts_lo = value;
+  else if (!strcmp(key, "corr_ts_hi")) mfn::tuning().corr_ts_hi = value;
   else if (!strcmp(key, "corr_dbg")) mfn::tuning().corr_dbg = value;
   else if (!strcmp(key, "corr_ring_th")) mfn::tuning().corr_ring_th = value;
   else if (!strcmp(key, "conv_umma")) mfn::tuning().conv_umma = value;

@@ -23,6 +23,7 @@ struct Tuning {
   int corr_rb = 1;            // 1: C > 32 correlations run on the row-block kernel (corr_rb.cu); 2: also C <= 32 when the TMA kernel declines; 0: chunked tile kernel
   int corr_tma = 1;           // 1: C <= 32 correlations run on the TMA pipeline kernel (corr_tma.cu) when the shape fits
   int warp_lin = 1;           // 1: mfn_warp_mask_forward_resample evaluates every pixel through linearity (warp_lin.cu); 0: border list
+  int corr_ts_lo = 0, corr_ts_hi = 0;   // development: device pointer (two halves) of the timeline buffer of corr_tma_kernel, 0 = off
   int corr_dbg = 0;           // profiling aid for the ring kernel: 2 = producers idle, 4 = no epilogue, 8 = no MMA (results invalid)
 };
 Tuning& tuning();

@@ -50,7 +50,7 @@ template <int WC, int NTN, bool PT>
 __global__ void __launch_bounds__(c3::NTHREADS, 1)
     conv3x3_mma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
                        const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
-                       int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int dil) {
+                       int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int dil, int lin_prefix) {
   using namespace c3;
   constexpr int WR = 8 / WC;
   constexpr int TROWS = PT ? WR : WR + 2;          // rows of the input tile
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const int xx = x0 + 16 * mt + g + 8 * (i >> 1);
-        if (xx < W) on[(size_t)f * plane + xx] = leaky(acc[mt][nt][i] + b, slope);
+        if (xx < W) on[(size_t)f * plane + xx] = leaky(acc[mt][nt][i] + b, f < lin_prefix ? 1.f : slope);
       }
     }
   }
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(c3::NTHREADS, 1)
 
 template <int WC, int NTN, bool PT>
 static int launch_conv_impl(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
-                            long long out_bs, int N, int Cin, int H, int W, int Cout, int dil, float slope,
+                            long long out_bs, int N, int Cin, int H, int W, int Cout, int dil, float slope, int lin_prefix,
                             cudaStream_t st) {
   using namespace c3;
   constexpr int WR = 8 / WC;
@@ -266,15 +266,16 @@ static int launch_conv_impl(const float* x, long long x_bs, const unsigned char*
   }
   const unsigned grid = (unsigned)((long long)N * tilesX * tilesY);
   conv3x3_mma_kernel<WC, NTN, PT><<<grid, NTHREADS, smem, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, Cout,
-                                                               CoutP, nChunks, slope, tilesX, tilesY, dil);
+                                                               CoutP, nChunks, slope, tilesX, tilesY, dil, lin_prefix);
   return check_launch(PT ? "conv3x3_mma_kernel<per-tap tiles>" : "conv3x3_mma_kernel<halo tile>");
 }
 
 template <int WC, int NTN>
 static int launch_conv(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
-                       long long out_bs, int N, int Cin, int H, int W, int Cout, int dil, float slope, cudaStream_t st) {
-  return dil == 1 ? launch_conv_impl<WC, NTN, false>(x, x_bs, wpack, bias, out, out_bs, N, Cin, H, W, Cout, 1, slope, st)
-                  : launch_conv_impl<WC, NTN, true>(x, x_bs, wpack, bias, out, out_bs, N, Cin, H, W, Cout, dil, slope, st);
+                       long long out_bs, int N, int Cin, int H, int W, int Cout, int dil, float slope, int lin_prefix,
+                       cudaStream_t st) {
+  return dil == 1 ? launch_conv_impl<WC, NTN, false>(x, x_bs, wpack, bias, out, out_bs, N, Cin, H, W, Cout, 1, slope, lin_prefix, st)
+                  : launch_conv_impl<WC, NTN, true>(x, x_bs, wpack, bias, out, out_bs, N, Cin, H, W, Cout, dil, slope, lin_prefix, st);
 }
 
 // bytes of the mma.sync weight image (first region of the packed buffer; the tcgen05 image follows it)
@@ -330,8 +331,11 @@ extern "C" int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, 
   MFN_REQUIRE(stride == 1 || (stride == 2 && dilation == 1), MFN_ERR_UNSUPPORTED,
               "mfn_conv3x3_forward: stride must be 1, or 2 with dilation 1 (got stride %d, dilation %d)", stride, dilation);
   MFN_REQUIRE(aligned(packed_weight, 16), MFN_ERR_ALIGNMENT, "mfn_conv3x3_forward: packed weights must be 16-byte aligned");
-  MFN_REQUIRE(out_mode == MFN_CONV_OUT_NCHW || (out_mode == MFN_CONV_OUT_DEPTH_TO_SPACE2 && stride == 1 && Cout % 4 == 0),
+  const int lin_prefix = out_mode >> 8, mode = out_mode & 0xff;
+  MFN_REQUIRE(mode == MFN_CONV_OUT_NCHW || (mode == MFN_CONV_OUT_DEPTH_TO_SPACE2 && stride == 1 && Cout % 4 == 0),
               MFN_ERR_INVALID_ARG, "mfn_conv3x3_forward: depth-to-space output needs stride 1 and Cout %% 4 == 0");
+  MFN_REQUIRE(lin_prefix >= 0 && lin_prefix <= Cout && (lin_prefix == 0 || mode == MFN_CONV_OUT_NCHW), MFN_ERR_INVALID_ARG,
+              "mfn_conv3x3_forward: linear prefix (out_mode >> 8 = %d) needs NCHW output and <= Cout", lin_prefix);
   const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
   const long long xbs = x_batch_stride ? x_batch_stride : (long long)Cin * H * W;
   const long long obs = out_batch_stride ? out_batch_stride : (long long)Cout * OH * OW;
@@ -339,7 +343,7 @@ extern "C" int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, 
               "mfn_conv3x3_forward: batch stride smaller than the tensor");
   const unsigned char* wp = static_cast<const unsigned char*>(packed_weight);
   cudaStream_t st = as_stream(stream);
-  const bool sync_ok = Cout <= 128 && stride == 1 && out_mode == MFN_CONV_OUT_NCHW;   // what the mma.sync kernels cover
+  const bool sync_ok = Cout <= 128 && stride == 1 && mode == MFN_CONV_OUT_NCHW;   // what the mma.sync kernels cover
   if ((tuning().conv_umma && W >= tuning().conv_umma_min_w) || !sync_ok) {   // tcgen05 / TMEM kernel
     const int rc = conv3x3_umma_launch(x, xbs, wp + conv3x3_sync_packed_bytes(Cin, Cout), bias, out, obs, N, Cin, H, W,
                                        Cout, stride, dilation, out_mode, leaky_slope, st);
@@ -348,8 +352,8 @@ extern "C" int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, 
                 Cout, stride, dilation);
   }
   const int nt = (Cout + 7) / 8;   // n8 tiles needed
-  if (nt <= 4) return launch_conv<1, 4>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, st);
-  if (nt <= 8) return launch_conv<1, 8>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, st);
-  if (nt <= 12) return launch_conv<2, 6>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, st);
-  return launch_conv<2, 8>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, st);
+  if (nt <= 4) return launch_conv<1, 4>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, lin_prefix, st);
+  if (nt <= 8) return launch_conv<1, 8>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, lin_prefix, st);
+  if (nt <= 12) return launch_conv<2, 6>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, lin_prefix, st);
+  return launch_conv<2, 8>(x, xbs, wp, bias, out, obs, N, Cin, H, W, Cout, dilation, leaky_slope, lin_prefix, st);
 }

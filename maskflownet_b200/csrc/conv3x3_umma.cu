@@ -190,8 +190,12 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
                         const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
                         int OH, int OW, int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int numTiles,
-                        int stride, int dil, int out_mode, int tmem_cols, int nacc, int ext) {
+                        int stride, int dil, int out_mode_arg, int tmem_cols, int nacc, int ext) {
   using namespace um;
+  // out_mode_arg = mode | (linear_prefix << 8): the first linear_prefix output channels are written WITHOUT the activation
+  // (a second, linear head sharing the input pass of an activated layer: network.py folds pred_flow / pred_mask over the
+  // dense block's input into its last convolution)
+  const int out_mode = out_mode_arg & 0xff, lin_prefix = out_mode_arg >> 8;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nslots = n_slots(stride, dil), PW = row_pitch(stride, dil), E = nslots * PW;
   const SmemMap sm = smem_map(E, CoutP);
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
               const int f = nc * 16 + jj;
               if (f < Cout && okp) {
                 const float b = bias ? __ldg(bias + f) : 0.f;
-                on[(size_t)f * oplane] = leaky(__uint_as_float(v[jj]) + b, slope);
+                on[(size_t)f * oplane] = leaky(__uint_as_float(v[jj]) + b, f < lin_prefix ? 1.f : slope);
               }
             }
           } else {
@@ -537,6 +541,7 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   using namespace um;
   if (Cout > 256 || (stride != 1 && !(stride == 2 && dil == 1))) return -1;
   if (ext != 0 && !((ext == 1 || ext == 2) && stride == 1 && dil == 1 && out_mode == 0)) return -1;
+  if ((out_mode >> 8) != 0 && (out_mode & 0xff) != 0) return -1;   // linear prefix only with plain NCHW output
   const int CoutP = um::cout_pad(Cout), nChunks = (Cin + 15) / 16;
   const int E = n_slots(stride, dil) * row_pitch(stride, dil);
   const SmemMap sm = smem_map(E, CoutP);

@@ -1018,7 +1018,11 @@ static int launch_mma(const float* d1, const float* d2, float* out, int N, int C
     const int rc = launch_corr_tma(MD, d1, d2, out, N, C, H, W, obs, slope, st);
     if (rc != -1) return rc;
   }
-  if (tuning().corr_rb && (C > 32 || !tuning().corr_tma || tuning().corr_rb > 1)) {   // row-block kernel (corr_rb.cu): all channels resident
+  // row-block kernel (corr_rb.cu, all channels resident, one CTA per output row block): wins on the SMALL levels, where the
+  // chunked tile kernel below starves the grid (levels 5 / 6: 24 / 16 tiles); measured slower on levels 3 / 4
+  // (profiles/r02_kbench_corr.jsonl), which therefore stay on the tile kernel.  corr_rb = 2 forces it for every shape.
+  const bool rb_small = (long long)N * H * W <= 4096;
+  if (tuning().corr_rb && ((C > 32 && rb_small) || tuning().corr_rb > 1)) {
     const int rc = launch_corr_rb(MD, d1, d2, out, N, C, H, W, obs, slope, st);
     if (rc != -1) return rc;
   }

@@ -66,7 +66,24 @@ class DeformParams(nn.Module):
         self.bias = nn.Parameter(torch.zeros(channels)) if use_bias else None
 
 
+class _Slab:
+    """Inference view of a dense block's output inside its concat buffer: x = buf[:, c0:], and -- when the block's last
+    convolution also produced them -- the linear heads' partial sums over everything but that convolution's own output
+    in buf[:, :c0] (see _FlowNetBase._dense_inplace)."""
+
+    def __init__(self, buf: torch.Tensor, c0: int, last_oc: int):
+        self.buf, self.c0, self.last_oc = buf, c0, last_oc
+
+    @property
+    def channels(self) -> int:
+        return self.buf.shape[1] - self.c0
+
+    def tensor(self) -> torch.Tensor:
+        return self.buf[:, self.c0:]
+
+
 class _FlowNetBase(nn.Module):
+    fuse_heads = True   # inference: pred_flow / pred_mask over the block input ride on conv{L}_4's input pass
     use_resample_warp = True   # inference: K3 through linearity (ops.warp_mask(resample=True)) at every level
     use_tc_conv = True   # inference: decoder / context 3x3 convolutions on the fp32-accurate tensor-core kernel (row N2)
 
@@ -89,21 +106,43 @@ class _FlowNetBase(nn.Module):
             cache[key] = (ver, build())
         return cache[key][1]
 
+    def _head_convs(self, lvl, with_mask):
+        pf = getattr(self, f"pred_flow{lvl}")
+        pm = getattr(self, f"pred_mask{lvl}") if with_mask and hasattr(self, f"pred_mask{lvl}") else None
+        return [pf] + ([pm] if pm is not None else [])
+
     def _heads(self, lvl, x, with_mask):
         """pred_flow{lvl} (2 channels) and pred_mask{lvl} (1 channel) read the same block output
-        (network/MaskFlownet.py:224, 226 ...): inference runs them as ONE 3-output convolution, no activation."""
-        pf = getattr(self, f"pred_flow{lvl}")
-        pm = getattr(self, f"pred_mask{lvl}") if with_mask else None
-        if not self._fast(x):
-            return pf(x), (pm(x) if pm is not None else None)
-        convs = [pf] + ([pm] if pm is not None else [])
+        (network/MaskFlownet.py:224, 226 ...): inference runs them as ONE 3-output convolution, no activation -- and, when
+        the dense block left their partial sums (a _Slab with c0 > 0), only over the block's last 32 channels."""
+        convs = self._head_convs(lvl, with_mask)
+        pm = convs[1] if len(convs) > 1 else None
+        if not isinstance(x, _Slab):
+            if not self._fast(x):
+                return convs[0](x), (pm(x) if pm is not None else None)
+            x = _Slab(x, 0, 0)
+        nh = 2 + (1 if pm is not None else 0)
+        buf, c0 = x.buf, x.c0
+        N, _, H, W = buf.shape
+        if c0 == nh and x.last_oc:   # partial sums present: finish with the tiny convolution over conv{L}_4's output
+            oc = x.last_oc
 
-        def build():
-            w = torch.cat([c.weight.detach() for c in convs], dim=0).contiguous()
-            b = torch.cat([c.bias.detach() for c in convs], dim=0).contiguous()
-            return ops.conv3x3_pack(w), b
-        packed, b = self._packed_fn(f"heads{lvl}", [p for c in convs for p in (c.weight, c.bias)], build)
-        y = ops.conv3x3(x, packed, b, 2 + (1 if pm is not None else 0), 1.0)
+            def build_tail():
+                w = torch.cat([c.weight.detach()[:, :oc] for c in convs], dim=0).contiguous()
+                b = torch.cat([c.bias.detach() for c in convs], dim=0).contiguous()
+                return ops.conv3x3_pack(w), b
+            packed, b = self._packed_fn(f"heads_tail{lvl}", [p for c in convs for p in (c.weight, c.bias)], build_tail)
+            y = torch.empty((N, nh, H, W), device=buf.device, dtype=torch.float32)
+            ops.conv3x3_slices(buf, c0, oc, packed, b, y, 0, nh, 1.0)
+            y += buf[:, :nh]
+        else:
+            def build():
+                w = torch.cat([c.weight.detach() for c in convs], dim=0).contiguous()
+                b = torch.cat([c.bias.detach() for c in convs], dim=0).contiguous()
+                return ops.conv3x3_pack(w), b
+            packed, b = self._packed_fn(f"heads{lvl}", [p for c in convs for p in (c.weight, c.bias)], build)
+            y = torch.empty((N, nh, H, W), device=buf.device, dtype=torch.float32)
+            ops.conv3x3_slices(buf, c0, x.channels, packed, b, y, 0, nh, 1.0)
         if pm is None:
             return y, None
         return y[:, :2].contiguous(), y[:, 2:3].contiguous()
@@ -112,13 +151,15 @@ class _FlowNetBase(nn.Module):
         """feat = LeakyReLU(upfeat{lvl}(x)): ConvTranspose2d(4, 2, 1) as a 3x3 convolution + depth-to-space on the
         tensor-core kernel (ops.conv_transpose4x4_pack)."""
         up = getattr(self, f"upfeat{lvl}")
-        if not self._fast(x):
-            return tF.leaky_relu(up(x), SLOPE)
+        if not isinstance(x, _Slab):
+            if not self._fast(x):
+                return tF.leaky_relu(up(x), SLOPE)
+            x = _Slab(x, 0, 0)
         packed = self._packed_fn(f"upfeat{lvl}", [up.weight], lambda: ops.conv_transpose4x4_pack(up.weight))
-        N, C, H, W = x.shape
+        N, _, H, W = x.buf.shape
         F = up.out_channels
-        out = torch.empty((N, F, 2 * H, 2 * W), device=x.device, dtype=torch.float32)
-        ops.conv3x3_slices(x, 0, C, packed, up.bias, out, 0, 4 * F, SLOPE, depth_to_space=True)
+        out = torch.empty((N, F, 2 * H, 2 * W), device=x.buf.device, dtype=torch.float32)
+        ops.conv3x3_slices(x.buf, x.c0, x.channels, packed, up.bias, out, 0, 4 * F, SLOPE, depth_to_space=True)
         return out
 
     def _plain(self, name, x):
@@ -160,7 +201,7 @@ class _FlowNetBase(nn.Module):
         buffer, every convolution reads its input channels in place and writes its output in front of them."""
         if self._fast(x):
             N, Cb, H, W = x.shape
-            tot = sum(DECODER_CH)
+            tot = sum(DECODER_CH) + self._heads_front(lvl)
             buf = torch.empty((N, tot + Cb, H, W), device=x.device, dtype=torch.float32)
             buf[:, tot:].copy_(x)
             return self._dense_inplace(lvl, buf, tot)
@@ -168,20 +209,47 @@ class _FlowNetBase(nn.Module):
             x = torch.cat([tF.leaky_relu(getattr(self, f"conv{lvl}_{i}")(x), SLOPE), x], dim=1)
         return x
 
+    def _heads_front(self, lvl) -> int:
+        """Extra leading channels of the block's concat buffer that receive the heads' partial sums (0 = not fused)."""
+        if not self.fuse_heads:
+            return 0
+        return 2 + (1 if hasattr(self, f"pred_mask{lvl}") else 0)
+
     def _dense_inplace(self, lvl, buf, off):
-        """buf[:, off:] holds the block's input; returns buf filled front to back."""
+        """buf[:, off:] holds the block's input; fills buf front to back and returns the block output as a _Slab.
+        With fuse_heads the last convolution also carries the nh linear head channels over ITS input (everything the heads
+        read except that convolution's own 32 output channels): weights [W_heads[:, 32:] ; W_4], written as channels
+        [partial (nh, no activation) | conv{lvl}_4 (32, LeakyReLU)] -- one pass over the ~550-channel input instead of two."""
         Ctot = buf.shape[1]
+        nh = self._heads_front(lvl)
         for i, oc in enumerate(DECODER_CH):
             conv = getattr(self, f"conv{lvl}_{i}")
-            ops.conv3x3_slices(buf, off, Ctot - off, self._packed(f"conv{lvl}_{i}"), conv.bias, buf, off - oc, oc, SLOPE)
+            if i == len(DECODER_CH) - 1 and nh:
+                heads = self._head_convs(lvl, True)
+
+                def build():
+                    w = torch.cat([h.weight.detach()[:, oc:] for h in heads] + [conv.weight.detach()], dim=0).contiguous()
+                    b = torch.cat([torch.zeros(nh, device=w.device), conv.bias.detach()]).contiguous()
+                    return ops.conv3x3_pack(w), b
+                packed, b = self._packed_fn(f"conv{lvl}_4+heads", [conv.weight, conv.bias] + [h.weight for h in heads], build)
+                assert off - oc - nh == 0
+                ops.conv3x3_slices(buf, off, Ctot - off, packed, b, buf, 0, oc + nh, SLOPE, linear_prefix=nh)
+            else:
+                ops.conv3x3_slices(buf, off, Ctot - off, self._packed(f"conv{lvl}_{i}"), conv.bias, buf, off - oc, oc, SLOPE)
             off -= oc
-        return buf
+        return _Slab(buf, nh, DECODER_CH[-1] if nh else 0)
 
     def _context(self, x):
-        fast = self._fast(x)
+        fast = isinstance(x, _Slab) or self._fast(x)
         for i in range(1, 7):
             conv = getattr(self, f"dc_conv{i}")
-            if fast:
+            if isinstance(x, _Slab):      # first layer reads the block output in place
+                N, _, H, W = x.buf.shape
+                y = torch.empty((N, conv.out_channels, H, W), device=x.buf.device, dtype=torch.float32)
+                ops.conv3x3_slices(x.buf, x.c0, x.channels, self._packed(f"dc_conv{i}"), conv.bias, y, 0, conv.out_channels,
+                                   SLOPE, conv.dilation[0])
+                x = y
+            elif fast:
                 x = ops.conv3x3(x, self._packed(f"dc_conv{i}"), conv.bias, conv.out_channels, SLOPE, conv.dilation[0])
             else:
                 x = tF.leaky_relu(conv(x), SLOPE)
@@ -246,7 +314,8 @@ class MaskFlownetS(_FlowNetBase):
             corr = ops.correlation(f1, f2, pad_size=self.md, max_displacement=self.md, leaky_slope=SLOPE)
             return self._dense(lvl, torch.cat([corr] + extras, dim=1) if extras else corr)
         tot = D + sum(e.shape[1] for e in extras)
-        front = sum(DECODER_CH) if self.use_tc_conv else 0   # room for the dense block's outputs (written in place)
+        # room for the dense block's outputs (written in place) and the heads' partial sums
+        front = (sum(DECODER_CH) + self._heads_front(lvl)) if self.use_tc_conv else 0
         buf = torch.empty((N, front + tot, H, W), device=f1.device, dtype=torch.float32)
         hook = self.event_hook
         if hook is not None:

@@ -398,11 +398,12 @@ def conv3x3_pack(weight: torch.Tensor) -> torch.Tensor:
 
 def conv3x3_slices(buf_in: torch.Tensor, c_in0: int, Cin: int, packed: torch.Tensor, bias: Optional[torch.Tensor],
                    buf_out: torch.Tensor, c_out0: int, Cout: int, leaky_slope: float = 0.1, dilation: int = 1,
-                   stride: int = 1, depth_to_space: bool = False) -> None:
+                   stride: int = 1, depth_to_space: bool = False, linear_prefix: int = 0) -> None:
     """out = LeakyReLU(conv3x3(buf_in[:, c_in0:c_in0+Cin]) + bias) written to buf_out[:, c_out0:c_out0+Cout]; both buffers
     dense NCHW (they may be the same tensor: the dense block's concat buffer).  stride 2 (pad 1) = the pyramid's
     down-sampling convolutions: buf_out is then ((H-1)//2+1, (W-1)//2+1).  depth_to_space: the Cout = 4F conv channels
-    are written as F channels of a (2H, 2W) image (sub-pixel phases; see conv_transpose4x4_pack).  Inference only."""
+    are written as F channels of a (2H, 2W) image (sub-pixel phases; see conv_transpose4x4_pack).  linear_prefix: the first
+    k output channels skip the activation (MFN_CONV_OUT_LINEAR_PREFIX).  Inference only."""
     for t, nm in ((buf_in, "buf_in"), (buf_out, "buf_out")):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4):
             raise MaskflowError(f"conv3x3_slices: {nm} must be a contiguous CUDA float32 NCHW tensor")
@@ -423,7 +424,7 @@ def conv3x3_slices(buf_in: torch.Tensor, c_in0: int, Cin: int, packed: torch.Ten
     xin = ctypes.c_void_p(buf_in.data_ptr() + 4 * c_in0 * H * W)
     xout = ctypes.c_void_p(buf_out.data_ptr() + 4 * c_out0 * OH * OW)
     _call("mfn_conv3x3_forward_ex", buf_in.device, xin, Cti * H * W, _p(packed), _p(b), xout, Cto * OH * OW, N, Cin, H, W,
-          Cout, int(stride), int(dilation), 1 if depth_to_space else 0, float(leaky_slope))
+          Cout, int(stride), int(dilation), (1 if depth_to_space else 0) | (int(linear_prefix) << 8), float(leaky_slope))
 
 
 def conv_transpose4x4_as_conv3x3(weight: torch.Tensor) -> torch.Tensor:

@@ -214,3 +214,22 @@ def test_predict_any_size_matches_oracle_pipeline():
     ref = prepost_ref.postprocess(preds[-1].numpy(), 50, 100)
     assert np.abs(flow.cpu().numpy() - ref).max() < 5e-3
     assert np.abs(occ.cpu().numpy() - prepost_ref.postprocess(o[0].numpy(), 50, 100, False, False)).max() < 1e-3
+
+
+@pytest.mark.parametrize("cls", [network.MaskFlownetS, network.MaskFlownet])
+def test_fused_heads_equal_separate_heads(cls):
+    """fuse_heads (pred_flow / pred_mask partial sums computed by conv{L}_4's launch through the linear-prefix epilogue, plus a
+    32-channel tail convolution) == the separate 3-output head convolution over the whole block output."""
+    model = _named_model(cls)
+    a1, a2 = seeded_images(seed=13, n=2, h=64, w=128)
+    with torch.no_grad():
+        model.fuse_heads = True
+        if cls is network.MaskFlownet:
+            model.MaskFlownet_S.fuse_heads = True
+        fused = model(a1.cuda(), a2.cuda())[0]
+        model.fuse_heads = False
+        if cls is network.MaskFlownet:
+            model.MaskFlownet_S.fuse_heads = False
+        plain = model(a1.cuda(), a2.cuda())[0]
+    for f, p in zip(fused, plain):
+        assert (f - p).abs().max().item() <= 1e-4 * max(1.0, p.abs().max().item())

@@ -345,7 +345,7 @@ def test_correlation_mma_long_tile_runs(shape, md, cap, ring_th, engine):
     assert np.abs(got - ref).max() <= 1e-4, name
     if engine == "legacy":
         assert "corr_mma" in name, name
-    elif shape[1] > 32:
+    elif shape[1] > 32 and shape[0] * shape[2] * shape[3] <= 4096:
         assert "corr_rb_kernel" in name, name
     elif shape[3] % 4 == 0:
         assert "corr_tma_kernel" in name, name
@@ -631,3 +631,22 @@ def test_preprocess_postprocess_match_oracle(shape, resize, dtype):
     occ = rng.random((N, 1, hw[0] // 4, hw[1] // 4)).astype(np.float32)
     got = ops.postprocess(cu(occ), H, W, flip_channels=False, is_flow=False).cpu().numpy()
     assert np.abs(got - prepost_ref.postprocess(occ, H, W, False, False)).max() <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 196, 6, 8), (8, 64, 56, 128), (1, 96, 28, 64), (2, 16, 9, 15), (1, 35, 7, 16), (2, 32, 24, 40),
+                                   (4, 128, 18, 30), (1, 64, 13, 20)])
+@pytest.mark.parametrize("md", [4, 2])
+def test_correlation_row_block_kernel_forced(shape, md):
+    """corr_rb_kernel (all channels resident, RB output rows per CTA) on shapes the dispatcher would give to other kernels."""
+    rng = np.random.default_rng(33)
+    f1, f2 = feat(rng, shape), feat(rng, shape)
+    ref = cref.correlation_forward(f1, f2, pad_size=md, max_displacement=md, threads=8)
+    ref = np.where(ref > 0, ref, 0.1 * ref)
+    _lib.set_tuning("corr_rb", 2)
+    try:
+        got = ops.correlation(cu(f1), cu(f2), pad_size=md, max_displacement=md, leaky_slope=0.1, algo=ops.CORR_MMA_BF16X3)
+        name = _lib.last_kernel()
+    finally:
+        _lib.set_tuning("corr_rb", 1)
+    assert "corr_rb_kernel" in name, name
+    assert np.abs(got.cpu().numpy() - ref).max() <= 1e-4

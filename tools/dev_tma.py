@@ -60,7 +60,7 @@ def main():
         N, C, H, W = shape
         D = (2 * md + 1) ** 2
         out = torch.empty(N, D, H, W, device=dev)
-        for tma, rbk in ((1, 1), (2, 1), (0, 0)):     # compact step loop / fully unrolled / round-1 ring kernel
+        for tma, rbk in ((1, 1), (2, 1), (0, 0)):     # production kernel / its development build (switches compiled in) / round-1 ring kernel
             _lib.set_tuning("corr_tma", tma)
             _lib.set_tuning("corr_rb", rbk)
             fn = lambda: ops.correlation(f1, f2, pad_size=md, max_displacement=md, leaky_slope=0.1,  # noqa: E731
