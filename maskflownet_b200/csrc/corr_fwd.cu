@@ -161,14 +161,14 @@ __global__ void __launch_bounds__(64 * (2 * MD + 1))
 // Tensor-core kernel (bf16 hi/lo split, mma.sync.m16n8k16).
 // =====================================================================================================
 namespace tc {
-constexpr int TH = 6;    // tile rows
+constexpr int TH = 4;    // tile rows
 constexpr int TW = 32;   // tile pixels per row
 constexpr int CK = 32;   // channels per pipeline stage
 constexpr int RS = 2 * CK + 16;  // bytes per pixel row of a bf16 tile (80: odd multiple of 16 -> conflict-free ldmatrix)
 constexpr int HX = 4;    // horizontal halo carried in shared memory (always 4 so that rows stay 16B aligned)
 constexpr int HWP = TW + 2 * HX;  // 40 pixels per halo row
-constexpr int NCONS = 12;         // consumer warps: (row 0..5) x (16-pixel half 0..1)
-constexpr int NPROD = 4;          // producer warps
+constexpr int NCONS = 8;          // consumer warps: (row 0..3) x (16-pixel half 0..1)
+constexpr int NPROD = 8;          // producer warps (the profile of the 12 + 4 split showed the consumers waiting on them)
 constexpr int NTHREADS = 32 * (NCONS + NPROD);
 constexpr int OCT_PER_ROW = (TW + 16) / 8;  // aligned 8-pixel groups spanning [x0-8, x0+TW+8)
 constexpr int STG_STRIDE = 20;    // floats per dx row of the per-warp output staging buffer
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1)
         const bool c_ok0 = ca < C, c_ok1 = ca + 1 < C;
         const float* pc = base + (size_t)ca * plane;
         constexpr int NOR = HR * OCT_PER_ROW;  // octet-rows in this stage
-        constexpr int U = 7;  // 14 independent 16-byte loads per thread in flight
+        constexpr int U = 5;  // 10 independent 16-byte loads per thread in flight
         for (int o0 = pw; o0 < NOR; o0 += NPROD * U) {
           float4 v0[U], v1[U];
           int pxr[U], rr[U];
@@ -1014,15 +1014,18 @@ template <int MD>
 static int launch_mma(const float* d1, const float* d2, float* out, int N, int C, int H, int W, long long obs,
                       float slope, cudaStream_t st) {
   const bool vec = (W % 4 == 0) && aligned(d2, 16) && aligned(d1, 16);
+  if (tuning().corr_rb > 1) {   // tests: force the row-block kernel for every shape it can take
+    const int rc = launch_corr_rb(MD, d1, d2, out, N, C, H, W, obs, slope, st);
+    if (rc != -1) return rc;
+  }
   if (C <= 32 && tuning().corr_tma) {   // TMA-in / TMA-out pipeline (corr_tma.cu); -1 = shape or alignment does not fit
     const int rc = launch_corr_tma(MD, d1, d2, out, N, C, H, W, obs, slope, st);
     if (rc != -1) return rc;
   }
-  // row-block kernel (corr_rb.cu, all channels resident, one CTA per output row block): wins on the SMALL levels, where the
-  // chunked tile kernel below starves the grid (levels 5 / 6: 24 / 16 tiles); measured slower on levels 3 / 4
-  // (profiles/r02_kbench_corr.jsonl), which therefore stay on the tile kernel.  corr_rb = 2 forces it for every shape.
-  const bool rb_small = (long long)N * H * W <= 4096;
-  if (tuning().corr_rb && ((C > 32 && rb_small) || tuning().corr_rb > 1)) {
+  // row-block kernel (corr_rb.cu, all channels resident, one CTA per output row block): wins only on the smallest level
+  // (level 6: 7 x 16, where the chunked tile kernel below has 16 tiles of 7 channel chunks); measured slower elsewhere
+  // (profiles/r02_kbench_corr.jsonl), so levels 3-5 stay on the tile kernel.
+  if (tuning().corr_rb && C > 32 && (long long)N * H * W <= 1024) {
     const int rc = launch_corr_rb(MD, d1, d2, out, N, C, H, W, obs, slope, st);
     if (rc != -1) return rc;
   }

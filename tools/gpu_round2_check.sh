@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== dev_tma (sigma-permuted B)"; timeout 300 python tools/dev_tma.py 2>&1 | grep -v '"ok": true' | tail -10 | cut -c1-200
-echo "== dev_tma v1"; MFN_LIB_PATH=tools/ab/lib_v1.so timeout 300 python tools/dev_tma.py 2>&1 | grep -v '"ok": true' | tail -10 | cut -c1-200
-echo "== ncu corr L3 tile kernel"; MFN_TUNING=corr_rb=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:corr_mma_kernel -s 1 -c 1 -o gpurun_out/r02_corr_mma_tile_L3 -f python tools/prof_corr.py --level 3 > gpurun_out/ncu_corr3t.log 2>&1; tail -2 gpurun_out/ncu_corr3t.log
+echo "== full pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+echo "== conv profile"; timeout 300 python tools/conv_profile.py 2>&1 | head -40
+echo "== bench cascade"; timeout 600 python bench.py --config cascade --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r02_bench_cascade_1gpu.json | cut -c1-700
+echo "== bench fwdbwd"; timeout 600 python bench.py --config fwdbwd --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r02_bench_fwdbwd_1gpu.json | cut -c1-700
