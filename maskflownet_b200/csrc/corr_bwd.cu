@@ -38,24 +38,43 @@ __global__ void __launch_bounds__(k2::NT)
 
   const float* gon = go + (size_t)n * obs;
   const float* fon = fwd_out ? fwd_out + (size_t)n * obs : nullptr;
-  for (int e = tid; e < D * TH * TW; e += NT) {
-    const int xx = e % TW, rr = (e / TW) % TH, q = e / (TW * TH);
-    const int ey = q / G - MD, ex = q % G - MD;
-    int ys = y0 + rr, xsrc = x0 + xx, qs = q;
-    bool ok = ys < H && xsrc < W;
-    if (SIDE_B) {
-      qs = (MD - ey) * G + (MD - ex);
-      ys += ey;
-      xsrc += ex;
-      ok = ok && ys >= 0 && ys < H && xsrc >= 0 && xsrc < W;
+  // G tile: thread (warp w, lane) owns column xx = lane of the tile rows j = w + 8k, j = q * TH + rr  (rr = w & 3 and
+  // q = (w >> 2) + 2k).  Loads are issued in batches of 8 before any of them is consumed (the round-1 loop consumed each
+  // load at once: 65 % of the kernel's stall samples were that dependency, profiles/r02_ncu_corr_bwd_L2_summary.txt).
+  {
+    const int w = tid >> 5, xx = tid & 31, rr = w & 3;
+    constexpr int KQ = (D + 1) / 2;
+#pragma unroll 1
+    for (int k0 = 0; k0 < KQ; k0 += 8) {
+      float gv[8], fv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = (w >> 2) + 2 * (k0 + u);
+        gv[u] = 0.f;
+        fv[u] = 1.f;
+        if (q < D) {
+          const int ey = q / G - MD, ex = q % G - MD;
+          int ys = y0 + rr, xsrc = x0 + xx, qs = q;
+          bool ok = ys < H && xsrc < W;
+          if (SIDE_B) {
+            qs = (MD - ey) * G + (MD - ex);
+            ys += ey;
+            xsrc += ex;
+            ok = ok && ys >= 0 && ys < H && xsrc >= 0 && xsrc < W;
+          }
+          if (ok) {
+            const size_t i = (size_t)qs * plane + (size_t)ys * W + xsrc;
+            gv[u] = __ldg(gon + i);
+            if (fon) fv[u] = __ldg(fon + i);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = (w >> 2) + 2 * (k0 + u);
+        if (q < D) Gt[(q * TH + rr) * TW + xx] = fv[u] > 0.f ? gv[u] : gv[u] * slope;
+      }
     }
-    float v = 0.f;
-    if (ok) {
-      const size_t i = (size_t)qs * plane + (size_t)ys * W + xsrc;
-      v = __ldg(gon + i);
-      if (fon && !(__ldg(fon + i) > 0.f)) v *= slope;
-    }
-    Gt[e] = v;
   }
 
   const int qx = tid & 7, r = (tid >> 3) & 3, cg = tid >> 5;  // 8 quads x 4 rows x 8 channel groups of CPT
@@ -63,10 +82,29 @@ __global__ void __launch_bounds__(k2::NT)
   const float inv = 1.f / (float)C;
   for (int c0 = 0; c0 < C; c0 += CK) {
     __syncthreads();
-    for (int e = tid; e < CK * HR * HWD; e += NT) {
-      const int xx = e % HWD, yy = (e / HWD) % HR, c = c0 + e / (HWD * HR);
-      const int y = y0 - MD + yy, x = x0 - 4 + xx;
-      Xs[e] = (c < C && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(Xn + (size_t)c * plane + (size_t)y * W + x) : 0.f;
+    {   // X tile: warp w owns the rows rho = w + 8k (rho = channel * HR + halo row) of 40 floats: lane -> columns lane and
+        // (lanes < 8) 32 + lane; eight rows (16 loads) in flight per thread
+      const int w = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+      for (int k0 = 0; k0 < CK * HR / 8; k0 += 8) {
+        float va[8], vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rho = w + 8 * (k0 + u), cc = rho / HR, yy = rho - cc * HR;
+          const int c = c0 + cc, y = y0 - MD + yy;
+          const bool rok = c < C && y >= 0 && y < H;
+          const float* src = Xn + (size_t)c * plane + (size_t)y * W + (x0 - 4);
+          const int xa = x0 - 4 + lane, xb = x0 + 28 + lane;
+          va[u] = (rok && xa >= 0 && xa < W) ? __ldg(src + lane) : 0.f;
+          vb[u] = (rok && lane < 8 && xb < W) ? __ldg(src + 32 + lane) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rho = w + 8 * (k0 + u);
+          Xs[rho * HWD + lane] = va[u];
+          if (lane < 8) Xs[rho * HWD + 32 + lane] = vb[u];
+        }
+      }
     }
     __syncthreads();
     float acc[CPT][4];

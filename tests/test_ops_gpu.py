@@ -347,7 +347,7 @@ def test_correlation_mma_long_tile_runs(shape, md, cap, ring_th, engine):
         assert "corr_mma" in name, name
     elif shape[1] > 32 and shape[0] * shape[2] * shape[3] <= 1024:
         assert "corr_rb_kernel" in name, name
-    elif shape[3] % 4 == 0:
+    elif shape[1] <= 32 and shape[3] % 4 == 0:
         assert "corr_tma_kernel" in name, name
 
 
@@ -650,3 +650,30 @@ def test_correlation_row_block_kernel_forced(shape, md):
         _lib.set_tuning("corr_rb", 1)
     assert "corr_rb_kernel" in name, name
     assert np.abs(got.cpu().numpy() - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("shape,md", [((8, 32, 96, 128), 4), ((8, 64, 48, 64), 4), ((4, 32, 112, 256), 2), ((2, 196, 6, 8), 4)])
+def test_correlation_backward_behind_tensor_core_forward_full_shapes(shape, md):
+    """K2 at BASELINE configs[2] (batch 8, 512x384: level 2 = 96x128, level 3 = 48x64) and cascade (md = 2) shapes, with the
+    DEFAULT (tensor-core) forward in front of it -- the LeakyReLU mask of the backward is taken from that forward's output --
+    against the C oracle's analytic backward.  Tolerance 2e-4 x scale of the gradients (they reach ~1e-2 here)."""
+    rng = np.random.default_rng(71)
+    f1, f2 = feat(rng, shape), feat(rng, shape)
+    G = 2 * md + 1
+    go = rng.standard_normal((shape[0], G * G, shape[2], shape[3])).astype(np.float32)
+    t1, t2 = cu(f1).requires_grad_(), cu(f2).requires_grad_()
+    out = ops.correlation(t1, t2, pad_size=md, max_displacement=md, leaky_slope=0.1)     # algo AUTO -> tensor cores
+    assert "simt" not in _lib.last_kernel()
+    out.backward(cu(go))
+    fwd = cref.correlation_forward(f1, f2, pad_size=md, max_displacement=md, threads=8)
+    # the sign pattern of the forward may differ where |fwd| is within the tensor-core tolerance of zero: mask those out
+    sure = np.abs(fwd) > 2e-5
+    go_eff = go * np.where(fwd > 0, 1.0, 0.1).astype(np.float32)
+    got_fwd = out.detach().cpu().numpy()
+    flipped = (got_fwd > 0) != (fwd > 0)
+    assert not (flipped & sure).any()
+    go_eff = np.where(flipped, go * np.where(got_fwd > 0, 1.0, 0.1), go_eff).astype(np.float32)
+    r1, r2 = cref.correlation_backward(go_eff, f1, f2, md, threads=8)
+    s = max(1.0, float(np.abs(r1).max()), float(np.abs(r2).max()))
+    assert np.abs(t1.grad.cpu().numpy() - r1).max() <= 2e-4 * s
+    assert np.abs(t2.grad.cpu().numpy() - r2).max() <= 2e-4 * s

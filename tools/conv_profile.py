@@ -17,8 +17,8 @@ def wrap(name, keyfn):
         records.append((name, keyfn(*args, **kw), e0, e1))
         return r
     setattr(ops, name, f)
-wrap("conv3x3_slices", lambda bi, c0, Cin, p, bias, bo, o0, Cout, slope=0.1, dilation=1, stride=1, depth_to_space=False:
-     f"{Cin}->{Cout} {bi.shape[2]}x{bi.shape[3]} N{bi.shape[0]} s{stride} d{dilation}{' d2s' if depth_to_space else ''}")
+wrap("conv3x3_slices", lambda bi, c0, Cin, p, bias, bo, o0, Cout, slope=0.1, dilation=1, stride=1, depth_to_space=False, linear_prefix=0:
+     f"{Cin}->{Cout} {bi.shape[2]}x{bi.shape[3]} N{bi.shape[0]} s{stride} d{dilation}{' d2s' if depth_to_space else ''}{' lin' + str(linear_prefix) if linear_prefix else ''}")
 wrap("correlation", lambda f1, f2, **kw: f"C{f1.shape[1]} {f1.shape[2]}x{f1.shape[3]}")
 wrap("warp_mask", lambda x, *a, **kw: f"C{x.shape[1]} {x.shape[2]}x{x.shape[3]} {'resample' if kw.get('resample') else ('tc' if kw.get('packed_weight') is not None else 'simt')}")
 with torch.no_grad():
