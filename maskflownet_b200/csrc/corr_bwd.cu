@@ -13,9 +13,10 @@
 
 namespace mfn {
 namespace k2 {
-// CTA = 4 rows x 32 pixels; thread = one 4-pixel quad x CPT channels: every G quad read from shared memory feeds CPT
-// channels (the round-1 kernel, one channel per thread, moved 5.3 bytes of shared memory per FMA; this one 2.3).
-constexpr int TH = 4, TW = 32, CPT = 4, CK = 8 * CPT, NT = 256;
+// CTA = 4 rows x 32 pixels; thread = one 4-pixel quad x CPT channels (CPT = 1: 56 KB of shared memory, four CTAs per SM --
+// measured faster than CPT = 4 with two CTAs per SM: the kernel is bound by the latency of its tile loads, not by the
+// shared-memory traffic of the stencil, profiles/r02_ncu_corr_bwd_L2_summary.txt).
+constexpr int TH = 4, TW = 32, CPT = 1, CK = 8 * CPT, NT = 256;
 }
 
 template <int MD, bool SIDE_B>
@@ -86,10 +87,13 @@ __global__ void __launch_bounds__(k2::NT)
         // (lanes < 8) 32 + lane; eight rows (16 loads) in flight per thread
       const int w = tid >> 5, lane = tid & 31;
 #pragma unroll 1
-      for (int k0 = 0; k0 < CK * HR / 8; k0 += 8) {
-        float va[8], vb[8];
+      constexpr int XB = 4;   // rows per batch: CK * HR / 8 rows per warp (12 or 8 with CPT = 1) in batches of 4
+      static_assert((CK * HR / 8) % XB == 0, "row batches");
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+      for (int k0 = 0; k0 < CK * HR / 8; k0 += XB) {
+        float va[XB], vb[XB];
+#pragma unroll
+        for (int u = 0; u < XB; ++u) {
           const int rho = w + 8 * (k0 + u), cc = rho / HR, yy = rho - cc * HR;
           const int c = c0 + cc, y = y0 - MD + yy;
           const bool rok = c < C && y >= 0 && y < H;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(k2::NT)
           vb[u] = (rok && lane < 8 && xb < W) ? __ldg(src + 32 + lane) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < XB; ++u) {
           const int rho = w + 8 * (k0 + u);
           Xs[rho * HWD + lane] = va[u];
           if (lane < 8) Xs[rho * HWD + 32 + lane] = vb[u];

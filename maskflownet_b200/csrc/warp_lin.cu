@@ -124,11 +124,36 @@ __global__ void __launch_bounds__(256)
     const float* yp = Yall + ((size_t)n * F + f0) * aplane;
     float* op = out + ((size_t)n * F + f0) * plane + pix;
     const float* tp = tradeoff ? tradeoff + ((size_t)n * F + f0) * plane + pix : nullptr;
-#pragma unroll 4
-    for (int f = f0; f < f1; ++f, yp += aplane, op += plane) {
-      float v = 0.f;
-      if (anyz) v = w00 * __ldg(yp + o00) + w01 * __ldg(yp + o01) + w10 * __ldg(yp + o10) + w11 * __ldg(yp + o11);
-      if (BORDER == MFN_BORDER_MXNET15 && (bh.any || bw.any)) {
+    if (!(BORDER == MFN_BORDER_MXNET15 && (bh.any || bw.any))) {
+      // plain pixels (all of them under the zero-corner rule): branch-free channel loop -- the four corner offsets are
+      // clamped into the array and the weights of out-of-range corners are zero, so every load is legal and the compiler
+      // batches the loads of eight channels before the first use (the first version, with the band test inside the
+      // loop, ran at 128 registers and one channel's loads in flight: profiles/r02_ncu_warp_lin_L3_summary.txt)
+      const int nf = f1 - f0;
+#pragma unroll 1
+      for (int fb = 0; fb < nf; fb += 8) {
+        float v[8], tv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool on = fb + u < nf;
+          const float* q = yp + (size_t)(on ? fb + u : 0) * aplane;
+          v[u] = w00 * __ldg(q + o00) + w01 * __ldg(q + o01) + w10 * __ldg(q + o10) + w11 * __ldg(q + o11);
+          tv[u] = (tp && on) ? __ldg(tp + (size_t)(fb + u) * plane) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (fb + u < nf) {
+            float r = v[u];
+            if (bias) r += __ldg(bias + f0 + fb + u);
+            r = r * sig + tv[u];
+            op[(size_t)(fb + u) * plane] = leaky(r, slope);
+          }
+        }
+      }
+    } else {
+      for (int f = f0; f < f1; ++f, yp += aplane, op += plane) {
+        float v = 0.f;
+        if (anyz) v = w00 * __ldg(yp + o00) + w01 * __ldg(yp + o01) + w10 * __ldg(yp + o10) + w11 * __ldg(yp + o11);
 #pragma unroll
         for (int i = 0; i < 3; ++i)    // tap row i in a band: + a_i * lerp_w of the band row's 1-D convolution
           if (bh.a[i] != 0.f) v += bh.a[i] * lerp_ext(yp + (size_t)(H + 4 + 3 * bh.B[i] - i) * WA, W, w0, 1);
@@ -143,14 +168,14 @@ __global__ void __launch_bounds__(256)
               if (bh.a[i] != 0.f && bw.a[j] != 0.f)
                 v += bh.a[i] * bw.a[j] * __ldg(yp + (size_t)(H + 4 + 3 * bh.B[i] - i) * WA + (W + 4 + 3 * bw.B[j] - j));
         }
+        if (bias) v += __ldg(bias + f);
+        v *= sig;
+        if (tp) {
+          v += __ldg(tp);
+          tp += plane;
+        }
+        *op = leaky(v, slope);
       }
-      if (bias) v += __ldg(bias + f);
-      v *= sig;
-      if (tp) {
-        v += __ldg(tp);
-        tp += plane;
-      }
-      *op = leaky(v, slope);
     }
   }
 }

@@ -445,7 +445,10 @@ def centralize(img1: torch.Tensor, img2: torch.Tensor):
 def predict_flow(net: nn.Module, img1_u8: torch.Tensor, img2_u8: torch.Tensor) -> torch.Tensor:
     """uint8 image pairs (N,3,H,W), H and W multiples of 64 -> full-resolution flow (N,2,H,W), (y,x)-ordered, in pixels:
     /255, centralize, network, Upsample(4) of the finest prediction (network/pipeline.py:99,117-138)."""
-    a, b, _ = centralize(img1_u8.float() / 255.0, img2_u8.float() / 255.0)
+    if img1_u8.is_cuda and img1_u8.dtype == torch.uint8 and img1_u8.is_contiguous() and img2_u8.is_contiguous():
+        a, b, _ = ops.preprocess(img1_u8, img2_u8)        # /255 + centralize in one fused op (csrc/prepost.cu)
+    else:
+        a, b, _ = centralize(img1_u8.float() / 255.0, img2_u8.float() / 255.0)
     preds = net(a, b)[0]
     return ops.upsample(preds[-1], 4)
 

@@ -7,6 +7,7 @@ cap() {  # name kernel-regex skip args...
   timeout 300 $NCU -k regex:$rx -s $skip -c 1 -o gpurun_out/r02_$name -f python tools/prof_ops.py "$@" > gpurun_out/ncu_$name.log 2>&1
   tail -1 gpurun_out/ncu_$name.log
 }
+echo "== kbench bwd"; timeout 300 python tools/kbench.py --what bwd --levels 2,3 --iters 10 2>&1 | grep -v "^$" | cut -c1-200
 echo "== launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_launches_bench_timed_region.csv python bench.py --steps 2 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 > gpurun_out/r02_launches_bench.log 2>&1; tail -1 gpurun_out/r02_launches_bench.log | cut -c1-200
 cap corr_tma_L2 corr_tma_kernel 1 corr --level 2
 cap corr_tile_L3 corr_mma_kernel 1 corr --level 3
