@@ -52,18 +52,6 @@ __device__ __forceinline__ Band bands(int p, float d, int n) {
   return b;
 }
 
-// linear interpolation along one axis of a zero-extended table t[0 .. n+1] (entry v <-> position v - 1, element stride
-// `st`) at position q
-__device__ __forceinline__ float lerp_ext(const float* __restrict__ t, int n, float q, int st) {
-  const float fl = floorf(q);
-  const int i0 = (int)fl + 1;
-  const float l = q - fl;
-  float v = 0.f;
-  if (i0 >= 0 && i0 <= n + 1) v += (1.f - l) * __ldg(t + (size_t)i0 * st);
-  if (i0 + 1 >= 0 && i0 + 1 <= n + 1) v += l * __ldg(t + (size_t)(i0 + 1) * st);
-  return v;
-}
-
 // Yall = conv3x3_umma(ext = 2): (N, F, H + 8, W + 8); entry (r, v) <-> position (r - 1, v - 1) of the virtual image
 //   rows 0 .. H+1, cols 0 .. W+1   Yext (the extended convolution)
 //   rows H+4-i / H+7-i             the 1-D convolution of the first / last image row with weight row i   (Rrow)
@@ -124,57 +112,68 @@ __global__ void __launch_bounds__(256)
     const float* yp = Yall + ((size_t)n * F + f0) * aplane;
     float* op = out + ((size_t)n * F + f0) * plane + pix;
     const float* tp = tradeoff ? tradeoff + ((size_t)n * F + f0) * plane + pix : nullptr;
-    if (!(BORDER == MFN_BORDER_MXNET15 && (bh.any || bw.any))) {
-      // plain pixels (all of them under the zero-corner rule): branch-free channel loop -- the four corner offsets are
-      // clamped into the array and the weights of out-of-range corners are zero, so every load is legal and the compiler
-      // batches the loads of eight channels before the first use (the first version, with the band test inside the
-      // loop, ran at 128 registers and one channel's loads in flight: profiles/r02_ncu_warp_lin_L3_summary.txt)
-      const int nf = f1 - f0;
-#pragma unroll 1
-      for (int fb = 0; fb < nf; fb += 8) {
-        float v[8], tv[8];
+    // ---- MXNet-1.5 band terms as (offset, weight) pairs, computed ONCE per pixel: at most one tap row and one tap column
+    //      can sit in a band (bands are one pixel wide, taps one pixel apart, H, W >= 4): D x Z -> two entries along the
+    //      band row's 1-D convolution, Z x D -> two along the band column's, D x D -> the corner product
+    int eo[5] = {0, 0, 0, 0, 0};
+    float ew[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (BORDER == MFN_BORDER_MXNET15) {
+      float a = 0.f, b = 0.f;
+      int rI = 0, cJ = 0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const bool on = fb + u < nf;
-          const float* q = yp + (size_t)(on ? fb + u : 0) * aplane;
-          v[u] = w00 * __ldg(q + o00) + w01 * __ldg(q + o01) + w10 * __ldg(q + o10) + w11 * __ldg(q + o11);
-          tv[u] = (tp && on) ? __ldg(tp + (size_t)(fb + u) * plane) : 0.f;
+      for (int i = 0; i < 3; ++i)
+        if (bh.a[i] != 0.f) {
+          a = bh.a[i];
+          rI = H + 4 + 3 * bh.B[i] - i;
         }
 #pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (bw.a[j] != 0.f) {
+          b = bw.a[j];
+          cJ = W + 4 + 3 * bw.B[j] - j;
+        }
+      eo[0] = rI * WA + jc0;
+      ew[0] = c0 ? a * (1.f - lw) : 0.f;
+      eo[1] = rI * WA + jc1;
+      ew[1] = c1 ? a * lw : 0.f;
+      eo[2] = ic0 * WA + cJ;
+      ew[2] = r0 ? b * (1.f - lh) : 0.f;
+      eo[3] = ic1 * WA + cJ;
+      ew[3] = r1 ? b * lh : 0.f;
+      eo[4] = rI * WA + cJ;
+      ew[4] = a * b;
+    }
+    const bool warp_bands = BORDER == MFN_BORDER_MXNET15 && __any_sync(__activemask(), bh.any || bw.any);
+    // branch-free channel loop: the corner offsets are clamped into the array and the weights of out-of-range corners are
+    // zero, so every load is legal and the loads of eight channels are issued before the first use (the first version, with
+    // per-channel band tests, executed 534 instructions per channel and warp: profiles/r02_ncu_warp_lin_L3_summary.txt)
+    const int nf = f1 - f0;
+#pragma unroll 1
+    for (int fb = 0; fb < nf; fb += 8) {
+      float v[8], tv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool on = fb + u < nf;
+        const float* q = yp + (size_t)(on ? fb + u : 0) * aplane;
+        v[u] = w00 * __ldg(q + o00) + w01 * __ldg(q + o01) + w10 * __ldg(q + o10) + w11 * __ldg(q + o11);
+        tv[u] = (tp && on) ? __ldg(tp + (size_t)(fb + u) * plane) : 0.f;
+      }
+      if (warp_bands) {
+#pragma unroll
         for (int u = 0; u < 8; ++u) {
-          if (fb + u < nf) {
-            float r = v[u];
-            if (bias) r += __ldg(bias + f0 + fb + u);
-            r = r * sig + tv[u];
-            op[(size_t)(fb + u) * plane] = leaky(r, slope);
-          }
+          const float* q = yp + (size_t)(fb + u < nf ? fb + u : 0) * aplane;
+          v[u] += ew[0] * __ldg(q + eo[0]) + ew[1] * __ldg(q + eo[1]) + ew[2] * __ldg(q + eo[2]) + ew[3] * __ldg(q + eo[3]) +
+                  ew[4] * __ldg(q + eo[4]);
         }
       }
-    } else {
-      for (int f = f0; f < f1; ++f, yp += aplane, op += plane) {
-        float v = 0.f;
-        if (anyz) v = w00 * __ldg(yp + o00) + w01 * __ldg(yp + o01) + w10 * __ldg(yp + o10) + w11 * __ldg(yp + o11);
 #pragma unroll
-        for (int i = 0; i < 3; ++i)    // tap row i in a band: + a_i * lerp_w of the band row's 1-D convolution
-          if (bh.a[i] != 0.f) v += bh.a[i] * lerp_ext(yp + (size_t)(H + 4 + 3 * bh.B[i] - i) * WA, W, w0, 1);
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          if (bw.a[j] != 0.f) v += bw.a[j] * lerp_ext(yp + (W + 4 + 3 * bw.B[j] - j), H, h0, WA);
-        if (bh.any && bw.any) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-              if (bh.a[i] != 0.f && bw.a[j] != 0.f)
-                v += bh.a[i] * bw.a[j] * __ldg(yp + (size_t)(H + 4 + 3 * bh.B[i] - i) * WA + (W + 4 + 3 * bw.B[j] - j));
+      for (int u = 0; u < 8; ++u) {
+        if (fb + u < nf) {
+          float r = v[u];
+          if (bias) r += __ldg(bias + f0 + fb + u);
+          r = r * sig + tv[u];
+          op[(size_t)(fb + u) * plane] = leaky(r, slope);
         }
-        if (bias) v += __ldg(bias + f);
-        v *= sig;
-        if (tp) {
-          v += __ldg(tp);
-          tp += plane;
-        }
-        *op = leaky(v, slope);
       }
     }
   }
