@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(ct::NTHREADS, 1)
         for (int j = 0; j < nm + 2; ++j, ++i) {
           const int y = UR * (g0 - 1 + j);
           const bool has_f1 = (j >= 1 && j <= nm);
-#pragma unroll
+#pragma unroll 1
           for (int cg = 0; cg < 4; ++cg) {
             const int seq = 4 * i + cg, rs = seq % RAW_STAGES, fill = seq / RAW_STAGES;
             mbar_wait(bar(B_RAW_EMPTY + rs), (fill & 1) ^ 1);
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(ct::NTHREADS, 1)
         }
         unsigned char* f1d = sm + OFF_F1 + (unit & 1) * F1_STAGE;
         if (has_f1) mbar_wait(bar(B_F1_EMPTY + (unit & 1)), ((unit >> 1) & 1) ^ 1);
-#pragma unroll
+#pragma unroll 1
         for (int cg = 0; cg < 4; ++cg) {
           const int seq = 4 * i + cg, rs = seq % RAW_STAGES, fill = seq / RAW_STAGES;
           mbar_wait(bar(B_RAW_FULL + rs), fill & 1);
@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(ct::NTHREADS, 1)
         qbar[t] = bar(B_F2_EMPTY + qs);
       }
       auto frag = [&](int lr, uint32_t (&fh)[2][4], uint32_t (&fl)[2][4]) {
-        const uint32_t ra = qrow[lr >> 2] + (uint32_t)((lr & 3) * F2_ROW);
+        const int qq = lr >> 2;
+        const uint32_t ra = (qq == 0 ? qrow[0] : (qq == 1 ? qrow[1] : qrow[2])) + (uint32_t)((lr & 3) * F2_ROW);
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           ldsm_x4(ra + offA[kk], fh[kk]);
@@ -322,15 +323,17 @@ __global__ void __launch_bounds__(ct::NTHREADS, 1)
       int win[UR];   // win[r] = slot offset of dy-group t - r (sliding window; pure register renaming once unrolled)
 #pragma unroll
       for (int r = 0; r < UR; ++r) win[r] = 0;
-      frag(LR0, ah[0], al[0]);
-#pragma unroll
-      for (int t = 0; t < NLR; ++t) {
-        const int cur = t & 1;
-        if (t + 1 < NLR) frag(LR0 + t + 1, ah[cur ^ 1], al[cur ^ 1]);
-        // data2 row t (image row y0 - MD + t) serves pixel rows r with dy index d = t - r
+      // One step = data2 row t (image row y0 - MD + t), serving pixel rows r with dy index d = t - r.  The G - 3 steps in
+      // which all four pixel rows are served run as a RUNTIME loop (unrolled by two for the fragment double buffer); only
+      // the three ramp-up and three ramp-down steps are unrolled with their compile-time row sets.  The fully unrolled walk
+      // (12 x ~105 instructions, 20 KB) plus the other roles' code overflowed the 32 KB instruction cache level: 15 % of the
+      // stall samples were "no instruction" (profiles/r02_ncu_corr_tma_L2_summary.txt).
+      auto step = [&](const int t, const bool all, const uint32_t (&fh)[2][4], const uint32_t (&fl)[2][4], uint32_t (&nh)[2][4],
+                      uint32_t (&nl)[2][4]) {
+        if (t + 1 < NLR) frag(LR0 + t + 1, nh, nl);
 #pragma unroll
         for (int r = UR - 1; r > 0; --r) win[r] = win[r - 1];
-        if (t < G) {   // dy-group t starts: take the next slot once the TMA store of its previous tenant has drained it
+        if (all || t < G) {   // dy-group t starts: take the next slot once the TMA store of its previous tenant has drained it
           win[0] = s_off;
           mbar_wait(stg_u32 + (uint32_t)s_off + STG_BAR_FREE, s_par ^ 1u);
           s_off += STG_SLOT;
@@ -348,34 +351,45 @@ __global__ void __launch_bounds__(ct::NTHREADS, 1)
         for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
           for (int r = 0; r < UR; ++r)
-            if (t - r >= 0 && t - r < G) mma_bf16(acc[r], ah[cur][kk], bq[r][kk][2], bq[r][kk][3]);
+            if (all || (t - r >= 0 && t - r < G)) mma_bf16(acc[r], fh[kk], bq[r][kk][2], bq[r][kk][3]);
 #pragma unroll
           for (int r = 0; r < UR; ++r)
-            if (t - r >= 0 && t - r < G) mma_bf16(acc[r], al[cur][kk], bq[r][kk][0], bq[r][kk][1]);
+            if (all || (t - r >= 0 && t - r < G)) mma_bf16(acc[r], fl[kk], bq[r][kk][0], bq[r][kk][1]);
 #pragma unroll
           for (int r = 0; r < UR; ++r)
-            if (t - r >= 0 && t - r < G) mma_bf16(acc[r], ah[cur][kk], bq[r][kk][0], bq[r][kk][1]);
+            if (all || (t - r >= 0 && t - r < G)) mma_bf16(acc[r], fh[kk], bq[r][kk][0], bq[r][kk][1]);
         }
 #pragma unroll
         for (int r = 0; r < UR; ++r) {
-          const int d = t - r;
-          if (d < 0 || d >= G) continue;
+          if (!(all || (t - r >= 0 && t - r < G))) continue;
           float v[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) v[q] = fmaxf(acc[r][q], acc[r][q] * slope);   // LeakyReLU for 0 <= slope <= 1
-          const float s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
           unsigned char* sl = stg + win[r];
-          if (ok[0]) *reinterpret_cast<float*>(sl + pre[0][r]) = s0;
-          if (ok[1]) *reinterpret_cast<float*>(sl + pre[1][r]) = s1;
-          if (ok[2]) *reinterpret_cast<float*>(sl + pre[0][r] + 1024) = s2;
-          if (ok[3]) *reinterpret_cast<float*>(sl + pre[1][r] + 1024) = s3;
+          if (ok[0]) *reinterpret_cast<float*>(sl + pre[0][r]) = v[0];
+          if (ok[1]) *reinterpret_cast<float*>(sl + pre[1][r]) = v[1];
+          if (ok[2]) *reinterpret_cast<float*>(sl + pre[0][r] + 1024) = v[2];
+          if (ok[3]) *reinterpret_cast<float*>(sl + pre[1][r] + 1024) = v[3];
         }
-        if (t >= UR - 1) {   // dy-group t - 3 received its last row from this warp
+        if (all || t >= UR - 1) {   // dy-group t - 3 received its last row from this warp
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(stg_u32 + (uint32_t)win[UR - 1] + STG_BAR_FULL);
         }
+      };
+      static_assert(UR == 4 && (G - 3) % 2 == 0 && NLR == G + 3, "step schedule");
+      frag(LR0, ah[0], al[0]);
+      step(0, false, ah[0], al[0], ah[1], al[1]);
+      step(1, false, ah[1], al[1], ah[0], al[0]);
+      step(2, false, ah[0], al[0], ah[1], al[1]);
+#pragma unroll 1
+      for (int t = UR - 1; t < G; t += 2) {
+        step(t, true, ah[1], al[1], ah[0], al[0]);
+        step(t + 1, true, ah[0], al[0], ah[1], al[1]);
       }
+      step(G, false, ah[1], al[1], ah[0], al[0]);
+      step(G + 1, false, ah[0], al[0], ah[1], al[1]);
+      step(G + 2, false, ah[1], al[1], ah[0], al[0]);
       // ---- this warp no longer reads the unit's three quanta ----
       __syncwarp();
       if (lane == 0) {
@@ -391,6 +405,7 @@ __global__ void __launch_bounds__(ct::NTHREADS, 1)
       for (int k = grp; k < K; k += 2) {
         const int gu = U0 + k, s = gu / Gs, g0 = gu - s * Gs;
         const int n = s / tilesX, x0 = (s - n * tilesX) * TW;
+#pragma unroll 1
         for (int d = 0; d < G; ++d, ++es) {
           const int slot = es % STG_SLOTS, fill = es / STG_SLOTS;
           const uint32_t sa = base + OFF_STG + (grp * STG_SLOTS + slot) * STG_SLOT;
