@@ -54,7 +54,7 @@ __host__ __device__ inline int smem_bytes(int C, int md, int rb_, int twb) {
 }  // namespace rb
 
 template <int MD, int RB, int TWB>
-__global__ void __launch_bounds__(rb::NTHREADS, 1)
+__global__ void __launch_bounds__(rb::NTHREADS, 2)
     corr_rb_kernel(const float* __restrict__ d1, const float* __restrict__ d2, float* __restrict__ out, int C, int H, int W,
                    long long out_bs, float slope, int tilesX, int tilesY) {
   using namespace rb;
@@ -214,8 +214,9 @@ static int launch_rb(const float* d1, const float* d2, float* out, int N, int C,
   const long long tiles = (long long)N * tilesX * tilesY;
   if (tiles >= (1LL << 31)) return -1;
   corr_rb_kernel<MD, RB, TWB><<<(unsigned)tiles, NTHREADS, smem, st>>>(d1, d2, out, C, H, W, obs, slope, tilesX, tilesY);
-  static const char* names[3] = {"corr_rb_kernel<rb1>", "corr_rb_kernel<rb2>", "corr_rb_kernel<rb4>"};
-  return check_launch(names[RB == 1 ? 0 : (RB == 2 ? 1 : 2)]);
+  static const char* names[6] = {"corr_rb_kernel<rb1,w32>", "corr_rb_kernel<rb2,w32>", "corr_rb_kernel<rb4,w32>",
+                                 "corr_rb_kernel<rb1,w16>", "corr_rb_kernel<rb2,w16>", "corr_rb_kernel<rb4,w16>"};
+  return check_launch(names[(RB == 1 ? 0 : (RB == 2 ? 1 : 2)) + (TWB == 2 ? 3 : 0)]);
 }
 
 // Returns -1 when no configuration fits the 227 KB of shared memory (caller falls back to the chunked tile kernel).
@@ -223,9 +224,11 @@ int launch_corr_rb(int md, const float* d1, const float* d2, float* out, int N, 
                    cudaStream_t st) {
   using namespace rb;
   const int budget = 227 * 1024;
-  const int twb = (W <= 16) ? 2 : 4;                    // 16-pixel strips for narrow images (half the data2 positions)
+  // 16-pixel strips for narrow images (half the data2 positions) -- or when forced (tuning "corr_rb_twb" = 2): the smaller
+  // tile lets two CTAs share an SM, so one CTA's load phase runs under the other's MMA phase
+  const int twb = (W <= 16 || tuning().corr_rb_twb == 2) ? 2 : 4;
   const int tilesX = (W + 8 * twb - 1) / (8 * twb);
-  int rbs = 4;
+  int rbs = tuning().corr_rb_rows > 0 ? tuning().corr_rb_rows : 4;
   auto ctas = [&](int r) { return (long long)N * tilesX * ((H + r - 1) / r); };
   while (rbs > 1 && (smem_bytes(C, md, rbs, twb) > budget || ctas(rbs) < kNumSMs)) rbs >>= 1;
   if (smem_bytes(C, md, rbs, twb) > budget) return -1;

@@ -1,3 +1,4 @@
 #!/bin/bash
+# round-2 GPU batch (edited per batch)
 mkdir -p gpurun_out
-echo "== dev_tma (compact + rolled producer/storer loops)"; timeout 300 python tools/dev_tma.py 2>&1 | grep -v '"ok": true' | grep -v "corr_mma_ring" | tail -8 | cut -c1-200
+echo "== dev_rb sweep"; timeout 600 python tools/dev_rb.py 2>&1 | tail -40 | cut -c1-300
