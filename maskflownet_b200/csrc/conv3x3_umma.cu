@@ -329,40 +329,57 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
         const uint32_t t0 = tmem_base + ((uint32_t)(32 * q) << 16) + acc * (uint32_t)R * row_cols + (uint32_t)r * row_cols;
 #pragma unroll 1
         for (int nc = 0; nc < CoutP / 16; ++nc) {
+          // The epilogue is a straight line: the TMEM loads, then the 16 (independent, L1-resident) bias loads under their
+          // latency, then arithmetic on all 16 channels, then predicated stores.  (Round 1 had one branch + one dependent
+          // bias load per channel: ~80 cycles x 16 channels per row made the NARROW layers epilogue-bound -- ncu of the
+          // 16 -> 16 pyramid layer: the issuers spun on acc_empty, the producers on a_empty.)
           uint32_t v[16];
           tmem_ld16(t0 + (uint32_t)(nc * 16), v);
-          if (FOLD) {   // second column block: the hi * lo term
-            uint32_t v2[16];
-            tmem_ld16(t0 + (uint32_t)(CoutP + nc * 16), v2);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t v2[16];
+          if (FOLD) tmem_ld16(t0 + (uint32_t)(CoutP + nc * 16), v2);   // second column block: the hi * lo term
+          float bv[16];
+          if (out_mode == 0) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int f = nc * 16 + jj;
+              bv[jj] = (bias != nullptr && f < Cout) ? __ldg(bias + f) : 0.f;
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (FOLD) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
           }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (out_mode == 0) {
-            float* on = out + (size_t)n * out_bs + (size_t)y * OW + xx;
+            float* on = out + (size_t)n * out_bs + (size_t)(nc * 16) * ((size_t)OH * OW) + (size_t)y * OW + xx;
             const size_t oplane = (size_t)OH * OW;
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
               const int f = nc * 16 + jj;
-              if (f < Cout && okp) {
-                const float b = bias ? __ldg(bias + f) : 0.f;
-                on[(size_t)f * oplane] = leaky(__uint_as_float(v[jj]) + b, f < lin_prefix ? 1.f : slope);
-              }
+              const float t = __uint_as_float(v[jj]) + bv[jj];
+              const float o = leaky(t, f < lin_prefix ? 1.f : slope);
+              if (f < Cout && okp) on[(size_t)jj * oplane] = o;
             }
           } else {
             // depth-to-space: conv channel f' = (2 py + px) * F + f  ->  out[n][f][2y + py][2x + px], out is (F, 2 OH, 2 OW)
             const int F = Cout >> 2;
             const size_t oplane = (size_t)(2 * OH) * (2 * OW);
+            float* on = out + (size_t)n * out_bs + (size_t)(2 * y) * (2 * OW) + 2 * xx;
+            int ph = (nc * 16) / F, f = nc * 16 - ph * F;          // running (phase, channel) of conv channel nc * 16 + jj
+            float bd[16];
+            int fo[16];
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-              const int fp = nc * 16 + jj;
-              if (fp < Cout && okp) {
-                const int ph = fp / F, f = fp - ph * F;
-                const float b = bias ? __ldg(bias + f) : 0.f;
-                out[(size_t)n * out_bs + (size_t)f * oplane + (size_t)(2 * y + (ph >> 1)) * (2 * OW) + 2 * xx + (ph & 1)] =
-                    leaky(__uint_as_float(v[jj]) + b, slope);
-              }
+              const bool okc = nc * 16 + jj < Cout;
+              bd[jj] = (bias != nullptr && okc) ? __ldg(bias + f) : 0.f;
+              fo[jj] = okc ? (f << 2) | ph : -1;
+              if (++f == F) { f = 0; ++ph; }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const float o = leaky(__uint_as_float(v[jj]) + bd[jj], slope);
+              if (fo[jj] >= 0 && okp)
+                on[(size_t)(fo[jj] >> 2) * oplane + (size_t)((fo[jj] >> 1) & 1) * (2 * OW) + (fo[jj] & 1)] = o;
             }
           }
         }

@@ -8,6 +8,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("what")
 ap.add_argument("--level", type=int, default=2)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--conv", default="16,16,224,512,16,1", help="conv: Cin,Cout,H,W,N,stride (input size)")
 a = ap.parse_args()
 L = a.level
 C = {6: 196, 5: 128, 4: 96, 3: 64, 2: 32}[L]
@@ -56,6 +57,14 @@ elif a.what == "warp_bwd":
         for t in (w, b, x, fc, mc, tr):
             t.grad = None
         o.backward(go, retain_graph=True)
+elif a.what == "conv":
+    ci, co, h, w_, n, st = (int(v) for v in a.conv.split(","))
+    xin = rn(n, ci, h, w_)
+    wt = rn(co, ci, 3, 3) * (2.0 / (9 * ci)) ** 0.5
+    pk = ops.conv3x3_pack(wt)
+    bo = torch.zeros(co, device=dev)
+    yout = torch.empty(n, co, (h - 1) // st + 1, (w_ - 1) // st + 1, device=dev)
+    fn = lambda: ops.conv3x3_slices(xin, 0, ci, pk, bo, yout, 0, co, 0.1, 1, st)  # noqa: E731
 else:
     raise SystemExit("unknown op " + a.what)
 with torch.set_grad_enabled(a.what.endswith("bwd")):
