@@ -34,7 +34,9 @@ constexpr int NPROD = 9;         // producer warps: 3, 8..15
 constexpr int NISSUE = R;        // MMA-issuing threads: one per output row (lane 0 of warps 0 and 2)
 constexpr int MAX_AS = 4, MAX_WS = 16;
 constexpr int BATCH = 4;         // producer items (32 entries x 8 channels) in flight per warp
-constexpr int BAR_BYTES = 512;   // a_full/a_empty [MAX_AS], w_full/w_empty [MAX_WS], acc_full/acc_empty [2], TMEM pointer
+constexpr int MAX_ACC = 8;       // accumulator sets in TMEM (narrow layers: 2 rows x 32 columns each -- a deep ring hides the
+                                 // commit -> epilogue -> acc_empty round trip, which is longer than such a tile's MMAs)
+constexpr int BAR_BYTES = 512;   // a_full/a_empty [MAX_AS], w_full/w_empty [MAX_WS], acc_full/acc_empty [MAX_ACC], TMEM pointer
 
 // Geometry of the converted input tile: `nslots` image rows of PW entries each.
 //   stride 1 (any dilation d): rows y0 - d .. y0 + R - 1 + d (or the 3R rows the taps touch when d >= R); entry p of a row is
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + sm.bar_off;
   const uint32_t a_full = bar0, a_empty = bar0 + 8 * MAX_AS, w_full = bar0 + 16 * MAX_AS, w_empty = w_full + 8 * MAX_WS,
-                 acc_full = w_empty + 8 * MAX_WS, acc_empty = acc_full + 16, tmem_ptr = acc_empty + 16;
+                 acc_full = w_empty + 8 * MAX_WS, acc_empty = acc_full + 8 * MAX_ACC, tmem_ptr = acc_empty + 8 * MAX_ACC;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + sm.bar_off + (tmem_ptr - bar0));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       mbar_init(w_full + 8 * i, 1);
       mbar_init(w_empty + 8 * i, NISSUE);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MAX_ACC; ++i) {
       mbar_init(acc_full + 8 * i, NISSUE);
       mbar_init(acc_empty + 8 * i, 4);
     }
@@ -339,10 +341,15 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
           if (FOLD) tmem_ld16(t0 + (uint32_t)(CoutP + nc * 16), v2);   // second column block: the hi * lo term
           float bv[16];
           if (out_mode == 0) {
+            if (bias != nullptr && nc * 16 + 16 <= Cout) {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int f = nc * 16 + jj;
-              bv[jj] = (bias != nullptr && f < Cout) ? __ldg(bias + f) : 0.f;
+              for (int jj = 0; jj < 16; ++jj) bv[jj] = __ldg(bias + nc * 16 + jj);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                const int f = nc * 16 + jj;
+                bv[jj] = (bias != nullptr && f < Cout) ? __ldg(bias + f) : 0.f;
+              }
             }
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -353,12 +360,24 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
           if (out_mode == 0) {
             float* on = out + (size_t)n * out_bs + (size_t)(nc * 16) * ((size_t)OH * OW) + (size_t)y * OW + xx;
             const size_t oplane = (size_t)OH * OW;
+            if (nc * 16 + 16 <= Cout && (lin_prefix <= nc * 16 || lin_prefix >= nc * 16 + 16)) {
+              // whole group valid, one activation: a running pointer and one predicated store per channel
+              const float sl = lin_prefix >= nc * 16 + 16 ? 1.f : slope;
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int f = nc * 16 + jj;
-              const float t = __uint_as_float(v[jj]) + bv[jj];
-              const float o = leaky(t, f < lin_prefix ? 1.f : slope);
-              if (f < Cout && okp) on[(size_t)jj * oplane] = o;
+              for (int jj = 0; jj < 16; ++jj) {
+                const float t = __uint_as_float(v[jj]) + bv[jj];
+                const float o = t > 0.f ? t : t * sl;
+                if (okp) *on = o;
+                on += oplane;
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                const int f = nc * 16 + jj;
+                const float t = __uint_as_float(v[jj]) + bv[jj];
+                const float o = leaky(t, f < lin_prefix ? 1.f : slope);
+                if (f < Cout && okp) on[(size_t)jj * oplane] = o;
+              }
             }
           } else {
             // depth-to-space: conv channel f' = (2 py + px) * F + f  ->  out[n][f][2y + py][2x + px], out is (F, 2 OH, 2 OW)
@@ -390,144 +409,121 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     }
   } else {
     // ============================ input producers (warps 3, 8..15) ============================
+    // One instruction stream for every layer shape: the (tile, chunk, batch) space of this CTA is walked as ONE flat
+    // sequence of batches (BATCH items of 32 entries x 8 channels per warp), software-pipelined over two register sets --
+    // the loads of batch i+1 (possibly the next chunk, possibly the next TILE) are in flight while batch i is converted and
+    // stored.  Round 1 pipelined only across the chunks of one tile: layers with one or two chunks (the pyramid's levels
+    // 1-2) paid a full DRAM round trip per tile.  Geometry is arithmetic only (e / PW through a multiply-high).
     const int pw = warp < 4 ? 0 : warp - 7;   // warp 3 -> 0, warps 8..15 -> 1..8
-    const int G = (E + 31) / 32, nItems = 2 * G;       // item = (32 entries, 8-channel plane)
-    uint32_t a_cnt = 0;
-    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-      const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+    const int G = (E + 31) / 32;
+    const bool one_plane = Cin <= 8;          // a single chunk whose channels 8..15 are zeros: plane 1 is cleared once, never loaded
+    const int nItems = one_plane ? G : 2 * G;                        // item = (32 entries, 8-channel plane)
+    const int nb = (nItems + NPROD * BATCH - 1) / (NPROD * BATCH);   // batches per stage (and warp)
+    const uint32_t pw_magic = 0xFFFFFFFFu / (uint32_t)PW + 1u;       // e / PW == umulhi(e, magic)  (e * PW < 2^32)
+    if (one_plane) {
+      for (int st = 0; st < AS; ++st)
+        for (int e = pw * 32 + lane; e < E; e += NPROD * 32) {
+          unsigned char* d = smem + st * sm.a_stage + (E + e) * 16;
+          *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(d + sm.a_lo) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    // load cursor (runs one batch ahead of the store cursor)
+    int l_tile = blockIdx.x, l_c = 0, l_kb = 0, l_x0 = 0, l_y0 = 0;
+    const float* l_xn = x;
+    auto set_tile = [&]() {
+      const int tx = l_tile % tilesX, ty = (l_tile / tilesX) % tilesY, n = l_tile / (tilesX * tilesY);
       // ext = 1: "full" convolution -- the output grid is the input grid extended by one pixel on every side
       // (OH = H + 2, OW = W + 2; output (y, x) sits at input position (y - 1, x - 1)); used by K3 through linearity
-      const int x0 = tx * MT - (ext ? 1 : 0), y0 = ty * R - (ext ? 1 : 0);
-      const float* xn = x + (size_t)n * x_bs;
-      // The producers are bound by their own instruction stream (ncu: ~150 integer instructions per item for the tile
-      // geometry), so when a chunk is one batch per warp (the common 2-row, dilation-1 tile) the per-item geometry -- source
-      // offset, validity, destination -- is computed ONCE per tile; per chunk only the channel plane advances.
-      const bool hoist = nItems <= NPROD * BATCH;
-      int goff[BATCH], soff[BATCH];
-      if (hoist) {
+      l_x0 = tx * MT - (ext ? 1 : 0);
+      l_y0 = ty * R - (ext ? 1 : 0);
+      l_xn = x + (size_t)n * x_bs;
+    };
+    auto advance = [&]() {   // false when this CTA's sequence is exhausted
+      if (++l_kb < nb) return true;
+      l_kb = 0;
+      if (++l_c < nChunks) return true;
+      l_c = 0;
+      l_tile += gridDim.x;
+      if (l_tile >= numTiles) return false;
+      set_tile();
+      return true;
+    };
+    auto load_batch = [&](float (&v)[BATCH][8]) {
+      const float* xc = l_xn + (size_t)(16 * l_c) * plane;
 #pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-          const int t = pw + b * NPROD;
-          const int kc = t & 1, e = (t >> 1) * 32 + lane;
-          const int slot = e / PW, pe = e - slot * PW;
-          int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(pe, x0, stride, dil);
-          if (ext == 2) {
-            y = y >= 0 ? band_map(y, H) : -1;
-            xx = xx >= 0 ? band_map(xx, W) : -1;
+      for (int b = 0; b < BATCH; ++b) {
+        const int t = pw + (l_kb * BATCH + b) * NPROD;
+        const int kc = one_plane ? 0 : (t & 1);
+        const int e = (one_plane ? t : (t >> 1)) * 32 + lane;
+        const int slot = (int)__umulhi((uint32_t)e, pw_magic), pe = e - slot * PW;
+        int y = row_of_slot(slot, l_y0, stride, dil), xx = x_of_entry(pe, l_x0, stride, dil);
+        if (ext == 2) {
+          y = y >= 0 ? band_map(y, H) : -1;
+          xx = xx >= 0 ? band_map(xx, W) : -1;
+        }
+        const bool ok = t < nItems && e < E && y >= 0 && y < H && xx >= 0 && xx < W;
+        const int c0 = 16 * l_c + 8 * kc;
+        const float* src = xc + (size_t)(8 * kc) * plane + (ok ? y * W + xx : 0);
+        if (c0 + 8 <= Cin) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            v[b][jj] = ok ? __ldg(src) : 0.f;
+            src += plane;
           }
-          const bool act = t < nItems && e < E;
-          const bool ok = act && y >= 0 && y < H && xx >= 0 && xx < W;
-          goff[b] = ok ? y * W + xx : -1;
-          soff[b] = act ? (kc * E + e) * 16 : -1;
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            v[b][jj] = (ok && c0 + jj < Cin) ? __ldg(src) : 0.f;
+            src += plane;
+          }
         }
       }
-      if (hoist) {
-        // chunk loop, software-pipelined over two register sets: the loads of chunk c+1 are in flight while chunk c is
-        // converted (bytes in flight = registers holding loads; one chunk per warp is only 4 KB)
-        auto load_chunk = [&](int c, float (&v)[BATCH][8]) {
-          const float* xc = xn + (size_t)(16 * c) * plane;
+    };
+    // store cursor: batch index inside the stage + the running position in the input ring
+    uint32_t as = 0, aph = 0;
+    bool wrapped = false;
+    auto store_batch = [&](int kb, const float (&v)[BATCH][8]) {
+      if (kb == 0 && wrapped) mbar_wait(a_empty + 8 * as, aph ^ 1);   // the MMAs that read this stage have completed
+      unsigned char* a_st = smem + as * sm.a_stage;
 #pragma unroll
-          for (int b = 0; b < BATCH; ++b) {
-            const int kc = (pw + b * NPROD) & 1;
-            const int c0 = 16 * c + 8 * kc;
-            const float* src = xc + (size_t)(8 * kc) * plane + (goff[b] >= 0 ? goff[b] : 0);
-            const bool ok = goff[b] >= 0;
-            if (c0 + 8 <= Cin) {
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                v[b][jj] = ok ? __ldg(src) : 0.f;
-                src += plane;
-              }
-            } else {
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                v[b][jj] = (ok && c0 + jj < Cin) ? __ldg(src) : 0.f;
-                src += plane;
-              }
-            }
-          }
-        };
-        auto store_chunk = [&](const float (&v)[BATCH][8]) {
-          const uint32_t as = a_cnt % (uint32_t)AS;
-          if (a_cnt >= (uint32_t)AS) mbar_wait(a_empty + 8 * as, ((a_cnt / (uint32_t)AS) + 1) & 1);
-          unsigned char* a_st = smem + as * sm.a_stage;
-#pragma unroll
-          for (int b = 0; b < BATCH; ++b) {
-            if (soff[b] >= 0) {
-              uint4 hi, lo;
-              split_pair(v[b][0], v[b][1], hi.x, lo.x);
-              split_pair(v[b][2], v[b][3], hi.y, lo.y);
-              split_pair(v[b][4], v[b][5], hi.z, lo.z);
-              split_pair(v[b][6], v[b][7], hi.w, lo.w);
-              unsigned char* dst = a_st + soff[b];
-              *reinterpret_cast<uint4*>(dst) = hi;
-              *reinterpret_cast<uint4*>(dst + sm.a_lo) = lo;
-            }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-          __syncwarp();
-          if (lane == 0) mbar_arrive(a_full + 8 * as);
-          ++a_cnt;
-        };
-        float va[BATCH][8], vb[BATCH][8];
-        load_chunk(0, va);
-        for (int c = 0; c < nChunks; c += 2) {
-          if (c + 1 < nChunks) load_chunk(c + 1, vb);
-          store_chunk(va);
-          if (c + 1 < nChunks) {
-            if (c + 2 < nChunks) load_chunk(c + 2, va);
-            store_chunk(vb);
-          }
+      for (int b = 0; b < BATCH; ++b) {
+        const int t = pw + (kb * BATCH + b) * NPROD;
+        const int kc = one_plane ? 0 : (t & 1);
+        const int e = (one_plane ? t : (t >> 1)) * 32 + lane;
+        if (t < nItems && e < E) {
+          uint4 hi, lo;
+          split_pair(v[b][0], v[b][1], hi.x, lo.x);
+          split_pair(v[b][2], v[b][3], hi.y, lo.y);
+          split_pair(v[b][4], v[b][5], hi.z, lo.z);
+          split_pair(v[b][6], v[b][7], hi.w, lo.w);
+          unsigned char* dst = a_st + (kc * E + e) * 16;
+          *reinterpret_cast<uint4*>(dst) = hi;
+          *reinterpret_cast<uint4*>(dst + sm.a_lo) = lo;
         }
-        continue;   // next tile
       }
-      for (int c = 0; c < nChunks; ++c, ++a_cnt) {
-        const uint32_t as = a_cnt % (uint32_t)AS;
-        if (a_cnt >= (uint32_t)AS) mbar_wait(a_empty + 8 * as, ((a_cnt / (uint32_t)AS) + 1) & 1);
-        unsigned char* a_st = smem + as * sm.a_stage;
-        {
-        }
-        for (int k0 = pw; k0 < nItems; k0 += NPROD * BATCH) {
-          float v[BATCH][8];
-#pragma unroll
-          for (int b = 0; b < BATCH; ++b) {
-            const int t = k0 + b * NPROD;
-            const int kc = t & 1, e = (t >> 1) * 32 + lane;
-            const int slot = e / PW, p = e - slot * PW;
-            int y = row_of_slot(slot, y0, stride, dil), xx = x_of_entry(p, x0, stride, dil);
-            if (ext == 2) {
-              y = y >= 0 ? band_map(y, H) : -1;
-              xx = xx >= 0 ? band_map(xx, W) : -1;
-            }
-            const bool ok = t < nItems && e < E && y >= 0 && y < H && xx >= 0 && xx < W;
-            const int c0 = 16 * c + 8 * kc;
-            const float* src = xn + (size_t)c0 * plane + (size_t)(ok ? y : 0) * W + (ok ? xx : 0);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              v[b][jj] = (ok && c0 + jj < Cin) ? __ldg(src) : 0.f;
-              src += plane;
-            }
-          }
-#pragma unroll
-          for (int b = 0; b < BATCH; ++b) {
-            const int t = k0 + b * NPROD;
-            const int kc = t & 1, e = (t >> 1) * 32 + lane;
-            if (t < nItems && e < E) {
-              uint4 hi, lo;
-              split_pair(v[b][0], v[b][1], hi.x, lo.x);
-              split_pair(v[b][2], v[b][3], hi.y, lo.y);
-              split_pair(v[b][4], v[b][5], hi.z, lo.z);
-              split_pair(v[b][6], v[b][7], hi.w, lo.w);
-              unsigned char* dst = a_st + (kc * E + e) * 16;
-              *reinterpret_cast<uint4*>(dst) = hi;
-              *reinterpret_cast<uint4*>(dst + sm.a_lo) = lo;
-            }
-          }
-        }
+      if (kb == nb - 1) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + 8 * as);
+        if (++as == (uint32_t)AS) { as = 0; aph ^= 1; wrapped = true; }
       }
+    };
+    float va[BATCH][8], vb[BATCH][8];
+    set_tile();
+    load_batch(va);
+    int s_kb = 0;
+    for (;;) {
+      bool more = advance();
+      if (more) load_batch(vb);
+      store_batch(s_kb, va);
+      if (!more) break;
+      s_kb = l_kb;
+      more = advance();
+      if (more) load_batch(va);
+      store_batch(s_kb, vb);
+      if (!more) break;
+      s_kb = l_kb;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -573,7 +569,10 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(conv3x3_umma_kernel): %s", cudaGetErrorString(e));
   }
   const int row_cols = fold_hi_lo(CoutP) ? 2 * CoutP : CoutP;   // TMEM columns per output row
-  const int nacc = 2 * R * row_cols <= 512 ? 2 : 1;   // double-buffered accumulators when they fit the 512 TMEM columns
+  // accumulator ring: as many sets as fit the 512 TMEM columns (2 at N = 128, 8 for the narrow layers), or the tuning cap
+  int nacc = 512 / (R * row_cols);
+  nacc = nacc < 1 ? 1 : (nacc > MAX_ACC ? MAX_ACC : nacc);
+  if (tuning().conv_nacc > 0 && nacc > tuning().conv_nacc) nacc = tuning().conv_nacc;
   int cols = 32;
   while (cols < nacc * R * row_cols) cols *= 2;
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
