@@ -243,6 +243,17 @@ MFN_API int mfn_conv3x3_forward(const float* x, long long x_batch_stride, const 
 MFN_API int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, const void* packed_weight, const float* bias,
                                    float* out, long long out_batch_stride, int N, int Cin, int H, int W, int Cout,
                                    int stride, int dilation, int out_mode, float leaky_slope, void* stream);
+/* mfn_conv3x3_forward_ws = mfn_conv3x3_forward_ex that may borrow a caller-owned fp32 scratch buffer: layers on the small
+ * pyramid levels (levels 5-6 of network/MaskFlownet.py: fewer output tiles than SMs, up to 43 input-channel chunks walked
+ * serially per tile) are then split over the input channels -- k CTAs per tile write partial sums to the workspace, a second
+ * launch adds them, the bias and the activation.  mfn_conv3x3_workspace_bytes returns the bytes that plan needs (0: the
+ * layer is not split; passing a smaller or null workspace simply runs the unsplit kernel).  Results differ from the
+ * unsplit kernel only by fp32 summation order. */
+MFN_API long long mfn_conv3x3_workspace_bytes(int N, int Cin, int H, int W, int Cout, int stride, int dilation);
+MFN_API int mfn_conv3x3_forward_ws(const float* x, long long x_batch_stride, const void* packed_weight, const float* bias,
+                                   float* out, long long out_batch_stride, int N, int Cin, int H, int W, int Cout,
+                                   int stride, int dilation, int out_mode, float leaky_slope, void* workspace,
+                                   long long workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * The step either side of the network.

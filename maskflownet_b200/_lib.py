@@ -39,6 +39,7 @@ SIGNATURES = {
     "mfn_conv3x3_pack_weights": [_f, _f, _i, _i, _f],
     "mfn_conv3x3_forward": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _fl, _f],
     "mfn_conv3x3_forward_ex": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _f],
+    "mfn_conv3x3_forward_ws": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _f, _ll, _f],
 }
 
 
@@ -69,6 +70,8 @@ def lib() -> ctypes.CDLL:
         L.mfn_launch_count.restype = ctypes.c_ulonglong
         L.mfn_conv3x3_packed_bytes.restype = ctypes.c_longlong
         L.mfn_conv3x3_packed_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.mfn_conv3x3_workspace_bytes.restype = ctypes.c_longlong
+        L.mfn_conv3x3_workspace_bytes.argtypes = [ctypes.c_int] * 7
         L.mfn_warp_resample_workspace_bytes.restype = ctypes.c_longlong
         L.mfn_warp_resample_workspace_bytes.argtypes = [ctypes.c_int] * 4
         for name, argtypes in SIGNATURES.items():

@@ -322,7 +322,26 @@ extern "C" int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, 
                                       const float* bias, float* out, long long out_batch_stride, int N, int Cin, int H,
                                       int W, int Cout, int stride, int dilation, int out_mode, float leaky_slope,
                                       void* stream) {
+  return mfn_conv3x3_forward_ws(x, x_batch_stride, packed_weight, bias, out, out_batch_stride, N, Cin, H, W, Cout, stride,
+                                dilation, out_mode, leaky_slope, nullptr, 0, stream);
+}
+
+extern "C" long long mfn_conv3x3_workspace_bytes(int N, int Cin, int H, int W, int Cout, int stride, int dilation) {
   using namespace mfn;
+  if (N <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0 || Cout > 256 || dilation < 1 ||
+      !(stride == 1 || (stride == 2 && dilation == 1)))
+    return 0;
+  if (!(tuning().conv_umma && W >= tuning().conv_umma_min_w) && Cout <= 128 && stride == 1) return 0;   // mma.sync kernel
+  return conv3x3_umma_workspace_bytes(N, Cin, H, W, Cout, stride, dilation);
+}
+
+extern "C" int mfn_conv3x3_forward_ws(const float* x, long long x_batch_stride, const void* packed_weight,
+                                      const float* bias, float* out, long long out_batch_stride, int N, int Cin, int H,
+                                      int W, int Cout, int stride, int dilation, int out_mode, float leaky_slope,
+                                      void* workspace, long long workspace_bytes, void* stream) {
+  using namespace mfn;
+  MFN_REQUIRE(workspace_bytes >= 0 && (workspace || workspace_bytes == 0) && aligned(workspace, 16), MFN_ERR_INVALID_ARG,
+              "mfn_conv3x3_forward_ws: workspace must be 16-byte aligned (or null with 0 bytes)");
   MFN_REQUIRE(x && packed_weight && out, MFN_ERR_INVALID_ARG, "mfn_conv3x3_forward: null pointer");
   MFN_REQUIRE(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, MFN_ERR_INVALID_ARG,
               "mfn_conv3x3_forward: non-positive extent");
@@ -346,7 +365,8 @@ extern "C" int mfn_conv3x3_forward_ex(const float* x, long long x_batch_stride, 
   const bool sync_ok = Cout <= 128 && stride == 1 && mode == MFN_CONV_OUT_NCHW;   // what the mma.sync kernels cover
   if ((tuning().conv_umma && W >= tuning().conv_umma_min_w) || !sync_ok) {   // tcgen05 / TMEM kernel
     const int rc = conv3x3_umma_launch(x, xbs, wp + conv3x3_sync_packed_bytes(Cin, Cout), bias, out, obs, N, Cin, H, W,
-                                       Cout, stride, dilation, out_mode, leaky_slope, st);
+                                       Cout, stride, dilation, out_mode, leaky_slope, st, 0, static_cast<float*>(workspace),
+                                       workspace_bytes);
     if (rc != -1) return rc;
     MFN_REQUIRE(sync_ok, MFN_ERR_UNSUPPORTED, "mfn_conv3x3_forward: shape fits neither kernel (Cout=%d stride=%d dilation=%d)",
                 Cout, stride, dilation);

@@ -190,13 +190,16 @@ __global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned c
 template <bool FOLD, int TPS>
 __global__ void __launch_bounds__(um::NTHREADS, 1)
     conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
-                        const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int Cin, int H, int W,
+                        const float* __restrict__ bias, float* __restrict__ out_base, long long out_bs, int Cin, int H, int W,
                         int OH, int OW, int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int numTiles,
-                        int stride, int dil, int out_mode_arg, int tmem_cols, int nacc, int ext) {
+                        int stride, int dil, int out_mode_arg, int tmem_cols, int nacc, int ext, int ksplit, long long part_stride) {
   using namespace um;
   // out_mode_arg = mode | (linear_prefix << 8): the first linear_prefix output channels are written WITHOUT the activation
   // (a second, linear head sharing the input pass of an activated layer: network.py folds pred_flow / pred_mask over the
   // dense block's input into its last convolution)
+  // ksplit > 1 (split-K, small images): `numTiles` counts WORK ITEMS w = tile * ksplit + part; part p walks the chunks
+  // [p nChunks / ksplit, (p + 1) nChunks / ksplit) and writes its raw partial sums to out + p * part_stride (the host passes
+  // a workspace, no bias, slope 1); conv3x3_umma_reduce_kernel adds the parts, the bias and the activation.
   const int out_mode = out_mode_arg & 0xff, lin_prefix = out_mode_arg >> 8;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nslots = n_slots(stride, dil), PW = row_pitch(stride, dil), E = nslots * PW;
@@ -210,7 +213,6 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t plane = (size_t)H * W;
-  const int nIter = nChunks * 9;
 
   if (tid == 0) {
     for (int i = 0; i < AS; ++i) {
@@ -264,7 +266,9 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
         if (j >= (uint32_t)nacc) mbar_wait(acc_empty + 8 * acc, accph ^ 1);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem_base + (acc * (uint32_t)R + (uint32_t)r) * row_cols;
-        for (int c = 0; c < nChunks; ++c) {
+        const int part = ksplit > 1 ? tile % ksplit : 0;
+        const int cb = part * nChunks / ksplit, ce = (part + 1) * nChunks / ksplit;
+        for (int c = cb; c < ce; ++c) {
           mbar_wait(a_full + 8 * as, aph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_st16 = s_base16 + as * a_stage16;
@@ -278,11 +282,11 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
             const uint64_t a_hi = desc_hi_a | (uint64_t)(a_st16 + a_off[tap]), a_lo = desc_hi_a | (uint64_t)(a_st16 + a_off[tap] + a_lo16);
             const uint64_t b_hi = desc_hi_b | (uint64_t)w16;
             if (FOLD) {
-              umma_bf16(d, a_hi, b_hi, idesc2, (tap == 0 && c == 0) ? 0u : 1u);   // [hi*hi | hi*lo]
+              umma_bf16(d, a_hi, b_hi, idesc2, (tap == 0 && c == cb) ? 0u : 1u);   // [hi*hi | hi*lo]
               umma_bf16(d, a_lo, b_hi, idesc, 1u);                                // += lo*hi into the first block
             } else {
               const uint64_t b_lo = desc_hi_b | (uint64_t)(w16 + w_half16);
-              umma_bf16(d, a_hi, b_lo, idesc, (tap == 0 && c == 0) ? 0u : 1u);
+              umma_bf16(d, a_hi, b_lo, idesc, (tap == 0 && c == cb) ? 0u : 1u);
               umma_bf16(d, a_lo, b_hi, idesc, 1u);
               umma_bf16(d, a_hi, b_hi, idesc, 1u);
             }
@@ -304,8 +308,10 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       uint32_t ws = 0, wph = 0;
       bool wrapped = false;
       for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        const unsigned char* src = wpack;
-        for (int it = 0; it < nIter; it += TPS, src += sm.w_stage) {
+        const int part = ksplit > 1 ? tile % ksplit : 0;
+        const int cb = part * nChunks / ksplit, ce = (part + 1) * nChunks / ksplit;
+        const unsigned char* src = wpack + (size_t)cb * 9 * sm.w_tile;
+        for (int it = 9 * cb; it < 9 * ce; it += TPS, src += sm.w_stage) {
           if (wrapped) mbar_wait(w_empty + 8 * ws, wph ^ 1);
           mbar_arrive_expect_tx(w_full + 8 * ws, (uint32_t)sm.w_stage);
           bulk_g2s(s_base + (uint32_t)sm.w_off + ws * (uint32_t)sm.w_stage, src, (uint32_t)sm.w_stage, w_full + 8 * ws);
@@ -318,7 +324,9 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     const int q = warp & 3;
     const uint32_t row_cols = (uint32_t)(FOLD ? 2 * CoutP : CoutP);
     uint32_t j = 0;
-    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
+    for (int work = blockIdx.x; work < numTiles; work += gridDim.x, ++j) {
+      const int tile = ksplit > 1 ? work / ksplit : work;
+      float* const out = out_base + (ksplit > 1 ? (size_t)(work - tile * ksplit) * (size_t)part_stride : (size_t)0);
       const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
       const uint32_t acc = j % (uint32_t)nacc;
       mbar_wait(acc_full + 8 * acc, (j / (uint32_t)nacc) & 1);
@@ -431,8 +439,16 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     // load cursor (runs one batch ahead of the store cursor)
     int l_tile = blockIdx.x, l_c = 0, l_kb = 0, l_x0 = 0, l_y0 = 0;
     const float* l_xn = x;
+    int l_ce = nChunks;        // end of this work item's chunk range (split-K)
     auto set_tile = [&]() {
-      const int tx = l_tile % tilesX, ty = (l_tile / tilesX) % tilesY, n = l_tile / (tilesX * tilesY);
+      int tl = l_tile;
+      if (ksplit > 1) {
+        tl = l_tile / ksplit;
+        const int part = l_tile - tl * ksplit;
+        l_c = part * nChunks / ksplit;
+        l_ce = (part + 1) * nChunks / ksplit;
+      }
+      const int tx = tl % tilesX, ty = (tl / tilesX) % tilesY, n = tl / (tilesX * tilesY);
       // ext = 1: "full" convolution -- the output grid is the input grid extended by one pixel on every side
       // (OH = H + 2, OW = W + 2; output (y, x) sits at input position (y - 1, x - 1)); used by K3 through linearity
       l_x0 = tx * MT - (ext ? 1 : 0);
@@ -442,40 +458,50 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     auto advance = [&]() {   // false when this CTA's sequence is exhausted
       if (++l_kb < nb) return true;
       l_kb = 0;
-      if (++l_c < nChunks) return true;
+      if (++l_c < l_ce) return true;
       l_c = 0;
       l_tile += gridDim.x;
       if (l_tile >= numTiles) return false;
       set_tile();
       return true;
     };
+    // Geometry without branches: y = ymul * y0 + ya + yb * (slot >> 1) + yc * (slot & 1) + yd * slot, x likewise (see
+    // row_of_slot / x_of_entry); addresses = one uniform 64-bit chunk base + 32-bit element offsets (16 planes < 2^32
+    // elements, checked by the host), so a load costs one add and one IMAD.WIDE instead of a 64-bit add chain.
+    const bool s2 = stride == 2, wide = !s2 && dil >= R;
+    const int ymul = s2 ? 2 : 1, ya = s2 ? -1 : -dil, yb = wide ? dil : 0, yc = wide ? 1 : 0, yd = wide ? 0 : 1;
+    const int xa = s2 ? 0 : -dil;
+    const uint32_t planeu = (uint32_t)plane;
     auto load_batch = [&](float (&v)[BATCH][8]) {
-      const float* xc = l_xn + (size_t)(16 * l_c) * plane;
+      const float* xc = l_xn + (size_t)(16 * l_c) * plane;   // warp-uniform
+      const int ybase = ymul * l_y0 + ya, xbase = ymul * l_x0 + xa;
 #pragma unroll
       for (int b = 0; b < BATCH; ++b) {
         const int t = pw + (l_kb * BATCH + b) * NPROD;
         const int kc = one_plane ? 0 : (t & 1);
         const int e = (one_plane ? t : (t >> 1)) * 32 + lane;
         const int slot = (int)__umulhi((uint32_t)e, pw_magic), pe = e - slot * PW;
-        int y = row_of_slot(slot, l_y0, stride, dil), xx = x_of_entry(pe, l_x0, stride, dil);
+        int y = ybase + yb * (slot >> 1) + yc * (slot & 1) + yd * slot;
+        const int q = (s2 && pe >= MT) ? 1 : 0;              // stride 2: odd-pixel block of the de-interleaved row
+        int xx = xbase + ymul * (pe - q * MT) - q;           // q = 1: 2 (x0 - 1 + pe - MT) + 1
         if (ext == 2) {
           y = y >= 0 ? band_map(y, H) : -1;
           xx = xx >= 0 ? band_map(xx, W) : -1;
         }
-        const bool ok = t < nItems && e < E && y >= 0 && y < H && xx >= 0 && xx < W;
+        const bool ok = t < nItems && e < E && (unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W;
         const int c0 = 16 * l_c + 8 * kc;
-        const float* src = xc + (size_t)(8 * kc) * plane + (ok ? y * W + xx : 0);
+        uint32_t off = (uint32_t)(8 * kc) * planeu + (ok ? (uint32_t)(y * W + xx) : 0u);
         if (c0 + 8 <= Cin) {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            v[b][jj] = ok ? __ldg(src) : 0.f;
-            src += plane;
+            v[b][jj] = ok ? __ldg(xc + off) : 0.f;
+            off += planeu;
           }
         } else {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            v[b][jj] = (ok && c0 + jj < Cin) ? __ldg(src) : 0.f;
-            src += plane;
+            v[b][jj] = (ok && c0 + jj < Cin) ? __ldg(xc + off) : 0.f;
+            off += planeu;
           }
         }
       }
@@ -547,10 +573,56 @@ int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int C
   return check_launch("conv3x3_pack_umma_kernel");
 }
 
+// Split-K second pass: out = act(sum_p parts[p] + bias), NCHW (with the linear prefix) or depth-to-space.
+__global__ void conv3x3_umma_reduce_kernel(const float* __restrict__ parts, int ksplit, long long part_stride,
+                                          const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int N,
+                                          int Cout, int OH, int OW, float slope, int out_mode_arg) {
+  const int out_mode = out_mode_arg & 0xff, lin_prefix = out_mode_arg >> 8;
+  const long long total = (long long)N * Cout * OH * OW;
+  const int F = Cout >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < ksplit; ++p) s += parts[(size_t)p * (size_t)part_stride + (size_t)i];
+    const int x = (int)(i % OW), y = (int)((i / OW) % OH), f = (int)((i / ((long long)OW * OH)) % Cout);
+    const int n = (int)(i / ((long long)OW * OH * Cout));
+    if (out_mode == 0) {
+      const float b = bias ? __ldg(bias + f) : 0.f;
+      out[(size_t)n * out_bs + ((size_t)f * OH + y) * OW + x] = leaky(s + b, f < lin_prefix ? 1.f : slope);
+    } else {
+      const int ph = f / F, ff = f - ph * F;
+      const float b = bias ? __ldg(bias + ff) : 0.f;
+      out[(size_t)n * out_bs + ((size_t)ff * (2 * OH) + (2 * y + (ph >> 1))) * (2 * OW) + 2 * x + (ph & 1)] = leaky(s + b, slope);
+    }
+  }
+}
+
+// Split-K plan: layers on the small pyramid levels have fewer tiles than SMs and a long, serial chunk walk per tile
+// (level 6: 32 tiles x up to 43 chunks, ~2 us per chunk from one issuing thread); k CTAs per tile take a k-th of the
+// chunks each.  Returns k (1 = no split).
+int conv3x3_umma_ksplit(int N, int Cin, int H, int W, int stride, int dil) {
+  using namespace um;
+  (void)dil;
+  if (!tuning().conv_splitk) return 1;
+  const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1, nChunks = (Cin + 15) / 16;
+  const long long tiles = (long long)N * ((OW + MT - 1) / MT) * ((OH + R - 1) / R);
+  int k = (int)(kNumSMs / tiles);
+  if (k > nChunks / 3) k = nChunks / 3;   // at least 3 chunks per part
+  if (k > 8) k = 8;
+  if (tuning().conv_splitk > 1 && k > tuning().conv_splitk) k = tuning().conv_splitk;
+  return k < 2 ? 1 : k;
+}
+
+long long conv3x3_umma_workspace_bytes(int N, int Cin, int H, int W, int Cout, int stride, int dil) {
+  const int k = conv3x3_umma_ksplit(N, Cin, H, W, stride, dil);
+  if (k < 2) return 0;
+  const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+  return (long long)k * N * Cout * OH * OW * 4;
+}
+
 // returns -1 when the shape does not fit this kernel (caller falls back to the mma.sync kernel)
 int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpack, const float* bias, float* out,
                         long long out_bs, int N, int Cin, int H, int W, int Cout, int stride, int dil, int out_mode,
-                        float slope, cudaStream_t st, int ext) {
+                        float slope, cudaStream_t st, int ext, float* ws, long long ws_bytes) {
   using namespace um;
   if (Cout > 256 || (stride != 1 && !(stride == 2 && dil == 1))) return -1;
   if (ext != 0 && !((ext == 1 || ext == 2) && stride == 1 && dil == 1 && out_mode == 0)) return -1;
@@ -559,6 +631,7 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   const int E = n_slots(stride, dil) * row_pitch(stride, dil);
   const SmemMap sm = smem_map(E, CoutP);
   if (sm.WS < 2 || E * 16 > 0x3FFF * 16) return -1;
+  if ((long long)H * W >= (1LL << 27)) return -1;   // the producers address a 16-plane chunk with 32-bit element offsets
   const int grow = ext == 2 ? 8 : 2 * ext;   // ext 1: grid + 1 pixel per side; ext 2: + the six band rows / columns too
   const int OH = stride == 2 ? (H - 1) / 2 + 1 : H + grow, OW = stride == 2 ? (W - 1) / 2 + 1 : W + grow;
   static SmemOptIn opt0, opt3, opt9;
@@ -576,13 +649,40 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   int cols = 32;
   while (cols < nacc * R * row_cols) cols *= 2;
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
-  const long long numTiles = (long long)N * tilesX * tilesY;
+  // split-K when the caller lent a workspace (plain grids only)
+  int ksplit = 1;
+  if (ws != nullptr && ext == 0) {
+    ksplit = conv3x3_umma_ksplit(N, Cin, H, W, stride, dil);
+    if (ksplit > 1 && ws_bytes < (long long)ksplit * N * Cout * OH * OW * 4) ksplit = 1;
+  }
+  const long long part_stride = (long long)N * Cout * OH * OW;
+  const long long numTiles = (long long)N * tilesX * tilesY * ksplit;
   const int cap = tuning().conv_grid_cap > 0 ? tuning().conv_grid_cap : kNumSMs;
   const unsigned grid = (unsigned)(numTiles < cap ? numTiles : cap);
+  if (ksplit > 1) {
+    // pass 1: raw partial sums, plain NCHW into the workspace; pass 2: reduce + bias + activation (+ depth-to-space)
+#define MFN_UMMA_SPLIT(FOLD_, TPS_)                                                                                        \
+  conv3x3_umma_kernel<FOLD_, TPS_><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, nullptr, ws, (long long)Cout * OH * OW, Cin, \
+                                                                     H, W, OH, OW, Cout, CoutP, nChunks, 1.f, tilesX, tilesY,      \
+                                                                     (int)numTiles, stride, dil, 0, cols, nacc, 0, ksplit,          \
+                                                                     part_stride)
+    if (taps_per_stage(CoutP) == 9) MFN_UMMA_SPLIT(true, 9);
+    else if (taps_per_stage(CoutP) == 3) MFN_UMMA_SPLIT(true, 3);
+    else MFN_UMMA_SPLIT(false, 1);
+#undef MFN_UMMA_SPLIT
+    const int rc = check_launch("conv3x3_umma_kernel");
+    if (rc != 0) return rc;
+    const long long total = part_stride;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    conv3x3_umma_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, ksplit, part_stride, bias, out, out_bs, N, Cout, OH, OW,
+                                                                slope, out_mode);
+    return check_launch("conv3x3_umma_reduce_kernel");
+  }
 #define MFN_UMMA_LAUNCH(FOLD_, TPS_)                                                                                       \
   conv3x3_umma_kernel<FOLD_, TPS_><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout,  \
                                                                      CoutP, nChunks, slope, tilesX, tilesY, (int)numTiles,      \
-                                                                     stride, dil, out_mode, cols, nacc, ext)
+                                                                     stride, dil, out_mode, cols, nacc, ext, 1, 0)
   if (taps_per_stage(CoutP) == 9) MFN_UMMA_LAUNCH(true, 9);
   else if (taps_per_stage(CoutP) == 3) MFN_UMMA_LAUNCH(true, 3);
   else MFN_UMMA_LAUNCH(false, 1);

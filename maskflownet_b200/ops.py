@@ -423,8 +423,12 @@ def conv3x3_slices(buf_in: torch.Tensor, c_in0: int, Cin: int, packed: torch.Ten
     _no_grad_path("conv3x3_slices", buf_in, b)
     xin = ctypes.c_void_p(buf_in.data_ptr() + 4 * c_in0 * H * W)
     xout = ctypes.c_void_p(buf_out.data_ptr() + 4 * c_out0 * OH * OW)
-    _call("mfn_conv3x3_forward_ex", buf_in.device, xin, Cti * H * W, _p(packed), _p(b), xout, Cto * OH * OW, N, Cin, H, W,
-          Cout, int(stride), int(dilation), (1 if depth_to_space else 0) | (int(linear_prefix) << 8), float(leaky_slope))
+    # split-K scratch for the layers of the small pyramid levels (0 bytes = the library does not split this shape)
+    ws_bytes = int(_lib.lib().mfn_conv3x3_workspace_bytes(N, Cin, H, W, Cout, int(stride), int(dilation)))
+    ws = torch.empty(ws_bytes // 4, device=buf_in.device, dtype=torch.float32) if ws_bytes else None
+    _call("mfn_conv3x3_forward_ws", buf_in.device, xin, Cti * H * W, _p(packed), _p(b), xout, Cto * OH * OW, N, Cin, H, W,
+          Cout, int(stride), int(dilation), (1 if depth_to_space else 0) | (int(linear_prefix) << 8), float(leaky_slope),
+          _p(ws), ws_bytes)
 
 
 def conv_transpose4x4_as_conv3x3(weight: torch.Tensor) -> torch.Tensor:

@@ -471,6 +471,48 @@ def test_conv_transpose4x4_as_conv3x3_depth_to_space(N, Cin, F, H, W):
     assert torch.isnan(out[:, :2]).all() and torch.isnan(out[:, 2 + F:]).all()      # neighbouring slices untouched
 
 
+@pytest.mark.parametrize("mode", ["nchw", "lin3", "d2s"])
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(8, 675, 64, 14, 32), (8, 529, 64, 7, 16), (8, 196, 196, 7, 16), (2, 100, 32, 9, 20)])
+def test_conv3x3_split_k_small_levels(N, Cin, Cout, H, W, mode):
+    """Levels 5-6 of the decoder (fewer tiles than SMs): the input-channel chunks are split over several CTAs per tile and
+    reduced by a second launch.  Against a float64 convolution and against the unsplit kernel, for the three epilogues
+    (NCHW, linear prefix, depth-to-space), into a slice of a wider buffer."""
+    rng = np.random.default_rng(53)
+    x = feat(rng, (N, Cin, H, W))
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    d2s = mode == "d2s"
+    F = Cout // 4 if d2s else Cout
+    b = (rng.standard_normal(F) * 0.1).astype(np.float32)
+    lin = 3 if mode == "lin3" else 0
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), None, padding=1)
+    if d2s:      # conv channel (2 py + px) * F + f -> out[f][2y + py][2x + px]
+        ref = ref.reshape(N, 2, 2, F, H, W).permute(0, 3, 4, 1, 5, 2).reshape(N, F, 2 * H, 2 * W)
+    ref = ref + torch.from_numpy(b).double().view(1, F, 1, 1)
+    act = torch.nn.functional.leaky_relu(ref, 0.1)
+    if lin:
+        act[:, :lin] = ref[:, :lin]
+    ref = act.float().numpy()
+    assert _lib.lib().mfn_conv3x3_workspace_bytes(N, Cin, H, W, Cout, 1, 1) > 0
+    packed = ops.conv3x3_pack(cu(w))
+    outs = []
+    for split in (1, 0):
+        _lib.set_tuning("conv_splitk", split)
+        try:
+            out = torch.full((N, F + 3, (2 if d2s else 1) * H, (2 if d2s else 1) * W), float("nan"), device=DEV)
+            before = _lib.launch_count()
+            ops.conv3x3_slices(cu(x), 0, Cin, packed, cu(b), out, 2, Cout, 0.1, depth_to_space=d2s, linear_prefix=lin)
+            launches = _lib.launch_count() - before
+            kern = _lib.last_kernel()
+        finally:
+            _lib.set_tuning("conv_splitk", 1)
+        assert (launches, "reduce" in kern) == ((2, True) if split else (1, False)), (launches, kern)
+        got = out[:, 2:2 + F].cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max())), (split, kern)
+        assert torch.isnan(out[:, :2]).all() and torch.isnan(out[:, 2 + F:]).all()
+        outs.append(got)
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-5 * max(1.0, float(np.abs(ref).max()))
+
+
 @pytest.mark.parametrize("cap", [1, 3])
 def test_conv3x3_persistent_tile_loop(cap):
     """The tcgen05 kernel is persistent: with the grid capped every CTA walks many tiles (stage rings wrap, barrier
