@@ -129,6 +129,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
+// Split-K plan (host: plan_split): work items [0, from) are whole tiles, the tiles [from, numTiles) are cut into k parts
+// over the channel chunks.  Their raw sums go to ws[part][n - n_lo][Cout][y - y_lo (rh rows)][OW].
+struct SplitK {
+  int k, from, n_lo, y_lo, rh;
+  long long part_stride;
+  float* ws;
+};
+struct Work {
+  int tile, part, cb, ce;   // part < 0: a whole tile
+};
+__device__ __forceinline__ Work decode_work(int w, const SplitK& sk, int nChunks) {
+  Work r;
+  if (sk.k <= 1 || w < sk.from) {
+    r.tile = w; r.part = -1; r.cb = 0; r.ce = nChunks;
+  } else {
+    const int u = w - sk.from, t = u / sk.k;
+    r.tile = sk.from + t;
+    r.part = u - t * sk.k;
+    r.cb = r.part * nChunks / sk.k;
+    r.ce = (r.part + 1) * nChunks / sk.k;
+  }
+  return r;
+}
+
 struct SmemMap {
   int a_lo, a_stage, w_tile, w_stage, w_off, bar_off, total, AS, WS;
 };
@@ -190,17 +214,17 @@ __global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned c
 template <bool FOLD, int TPS>
 __global__ void __launch_bounds__(um::NTHREADS, 1)
     conv3x3_umma_kernel(const float* __restrict__ x, long long x_bs, const unsigned char* __restrict__ wpack,
-                        const float* __restrict__ bias, float* __restrict__ out_base, long long out_bs, int Cin, int H, int W,
-                        int OH, int OW, int Cout, int CoutP, int nChunks, float slope, int tilesX, int tilesY, int numTiles,
-                        int stride, int dil, int out_mode_arg, int tmem_cols, int nacc, int ext, int ksplit, long long part_stride) {
+                        const float* __restrict__ bias_arg, float* __restrict__ out_base, long long out_bs, int Cin, int H, int W,
+                        int OH, int OW, int Cout, int CoutP, int nChunks, float slope_arg, int tilesX, int tilesY, int numTiles,
+                        int stride, int dil, int out_mode_arg, int tmem_cols, int nacc, int ext, um::SplitK sk) {
   using namespace um;
   // out_mode_arg = mode | (linear_prefix << 8): the first linear_prefix output channels are written WITHOUT the activation
   // (a second, linear head sharing the input pass of an activated layer: network.py folds pred_flow / pred_mask over the
   // dense block's input into its last convolution)
-  // ksplit > 1 (split-K, small images): `numTiles` counts WORK ITEMS w = tile * ksplit + part; part p walks the chunks
-  // [p nChunks / ksplit, (p + 1) nChunks / ksplit) and writes its raw partial sums to out + p * part_stride (the host passes
-  // a workspace, no bias, slope 1); conv3x3_umma_reduce_kernel adds the parts, the bias and the activation.
-  const int out_mode = out_mode_arg & 0xff, lin_prefix = out_mode_arg >> 8;
+  // Split-K (sk.k > 1): `numTiles` counts WORK ITEMS.  Items below sk.from are whole tiles; the tiles from sk.from on are
+  // cut into sk.k parts over the channel chunks -- part p walks chunks [p nChunks / k, (p + 1) nChunks / k) and writes its
+  // RAW partial sums (no bias, no activation) to the workspace; conv3x3_umma_reduce_kernel finishes that region.
+  const int out_mode_k = out_mode_arg & 0xff, lin_prefix_k = out_mode_arg >> 8;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nslots = n_slots(stride, dil), PW = row_pitch(stride, dil), E = nslots * PW;
   const SmemMap sm = smem_map(E, CoutP);
@@ -266,8 +290,8 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
         if (j >= (uint32_t)nacc) mbar_wait(acc_empty + 8 * acc, accph ^ 1);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem_base + (acc * (uint32_t)R + (uint32_t)r) * row_cols;
-        const int part = ksplit > 1 ? tile % ksplit : 0;
-        const int cb = part * nChunks / ksplit, ce = (part + 1) * nChunks / ksplit;
+        const Work wk = decode_work(tile, sk, nChunks);
+        const int cb = wk.cb, ce = wk.ce;
         for (int c = cb; c < ce; ++c) {
           mbar_wait(a_full + 8 * as, aph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -308,8 +332,8 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
       uint32_t ws = 0, wph = 0;
       bool wrapped = false;
       for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        const int part = ksplit > 1 ? tile % ksplit : 0;
-        const int cb = part * nChunks / ksplit, ce = (part + 1) * nChunks / ksplit;
+        const Work wk = decode_work(tile, sk, nChunks);
+        const int cb = wk.cb, ce = wk.ce;
         const unsigned char* src = wpack + (size_t)cb * 9 * sm.w_tile;
         for (int it = 9 * cb; it < 9 * ce; it += TPS, src += sm.w_stage) {
           if (wrapped) mbar_wait(w_empty + 8 * ws, wph ^ 1);
@@ -325,9 +349,18 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     const uint32_t row_cols = (uint32_t)(FOLD ? 2 * CoutP : CoutP);
     uint32_t j = 0;
     for (int work = blockIdx.x; work < numTiles; work += gridDim.x, ++j) {
-      const int tile = ksplit > 1 ? work / ksplit : work;
-      float* const out = out_base + (ksplit > 1 ? (size_t)(work - tile * ksplit) * (size_t)part_stride : (size_t)0);
+      const Work wk = decode_work(work, sk, nChunks);
+      const int tile = wk.tile;
       const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+      // a part of a split tile: raw sums into its slot of the workspace region [n_lo.., all channels, y_lo.., OW]
+      const bool partial = wk.part >= 0;
+      const float* const bias = partial ? nullptr : bias_arg;
+      const float slope = partial ? 1.f : slope_arg;
+      const int out_mode = partial ? 0 : out_mode_k, lin_prefix = partial ? 0 : lin_prefix_k;
+      const size_t oplane0 = partial ? (size_t)sk.rh * OW : (size_t)OH * OW;    // plane pitch of plain NCHW output
+      float* const out = partial ? sk.ws + (size_t)wk.part * (size_t)sk.part_stride + (size_t)(n - sk.n_lo) * Cout * oplane0 -
+                                       (size_t)sk.y_lo * OW
+                                 : out_base + (size_t)n * out_bs;
       const uint32_t acc = j % (uint32_t)nacc;
       mbar_wait(acc_full + 8 * acc, (j / (uint32_t)nacc) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -366,8 +399,8 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
             for (int jj = 0; jj < 16; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
           }
           if (out_mode == 0) {
-            float* on = out + (size_t)n * out_bs + (size_t)(nc * 16) * ((size_t)OH * OW) + (size_t)y * OW + xx;
-            const size_t oplane = (size_t)OH * OW;
+            const size_t oplane = oplane0;
+            float* on = out + (size_t)(nc * 16) * oplane + (size_t)y * OW + xx;
             if (nc * 16 + 16 <= Cout && (lin_prefix <= nc * 16 || lin_prefix >= nc * 16 + 16)) {
               // whole group valid, one activation: a running pointer and one predicated store per channel
               const float sl = lin_prefix >= nc * 16 + 16 ? 1.f : slope;
@@ -391,7 +424,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
             // depth-to-space: conv channel f' = (2 py + px) * F + f  ->  out[n][f][2y + py][2x + px], out is (F, 2 OH, 2 OW)
             const int F = Cout >> 2;
             const size_t oplane = (size_t)(2 * OH) * (2 * OW);
-            float* on = out + (size_t)n * out_bs + (size_t)(2 * y) * (2 * OW) + 2 * xx;
+            float* on = out + (size_t)(2 * y) * (2 * OW) + 2 * xx;
             int ph = (nc * 16) / F, f = nc * 16 - ph * F;          // running (phase, channel) of conv channel nc * 16 + jj
             float bd[16];
             int fo[16];
@@ -442,11 +475,11 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     int l_ce = nChunks;        // end of this work item's chunk range (split-K)
     auto set_tile = [&]() {
       int tl = l_tile;
-      if (ksplit > 1) {
-        tl = l_tile / ksplit;
-        const int part = l_tile - tl * ksplit;
-        l_c = part * nChunks / ksplit;
-        l_ce = (part + 1) * nChunks / ksplit;
+      if (sk.k > 1) {
+        const Work wk = decode_work(l_tile, sk, nChunks);
+        tl = wk.tile;
+        l_c = wk.cb;
+        l_ce = wk.ce;
       }
       const int tx = tl % tilesX, ty = (tl / tilesX) % tilesY, n = tl / (tilesX * tilesY);
       // ext = 1: "full" convolution -- the output grid is the input grid extended by one pixel on every side
@@ -573,18 +606,18 @@ int conv3x3_umma_pack(const float* weight, unsigned char* packed, int Cin, int C
   return check_launch("conv3x3_pack_umma_kernel");
 }
 
-// Split-K second pass: out = act(sum_p parts[p] + bias), NCHW (with the linear prefix) or depth-to-space.
-__global__ void conv3x3_umma_reduce_kernel(const float* __restrict__ parts, int ksplit, long long part_stride,
-                                          const float* __restrict__ bias, float* __restrict__ out, long long out_bs, int N,
-                                          int Cout, int OH, int OW, float slope, int out_mode_arg) {
+// Split-K second pass over the split region (samples n_lo.., rows y_lo..): out = act(sum_p parts[p] + bias), NCHW (with
+// the linear prefix) or depth-to-space.
+__global__ void conv3x3_umma_reduce_kernel(um::SplitK sk, int RN, const float* __restrict__ bias, float* __restrict__ out,
+                                           long long out_bs, int Cout, int OH, int OW, float slope, int out_mode_arg) {
   const int out_mode = out_mode_arg & 0xff, lin_prefix = out_mode_arg >> 8;
-  const long long total = (long long)N * Cout * OH * OW;
+  const long long total = (long long)RN * Cout * sk.rh * OW;
   const int F = Cout >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int p = 0; p < ksplit; ++p) s += parts[(size_t)p * (size_t)part_stride + (size_t)i];
-    const int x = (int)(i % OW), y = (int)((i / OW) % OH), f = (int)((i / ((long long)OW * OH)) % Cout);
-    const int n = (int)(i / ((long long)OW * OH * Cout));
+    for (int p = 0; p < sk.k; ++p) s += sk.ws[(size_t)p * (size_t)sk.part_stride + (size_t)i];
+    const int x = (int)(i % OW), y = sk.y_lo + (int)((i / OW) % sk.rh), f = (int)((i / ((long long)OW * sk.rh)) % Cout);
+    const int n = sk.n_lo + (int)(i / ((long long)OW * sk.rh * Cout));
     if (out_mode == 0) {
       const float b = bias ? __ldg(bias + f) : 0.f;
       out[(size_t)n * out_bs + ((size_t)f * OH + y) * OW + x] = leaky(s + b, f < lin_prefix ? 1.f : slope);
@@ -596,27 +629,53 @@ __global__ void conv3x3_umma_reduce_kernel(const float* __restrict__ parts, int 
   }
 }
 
-// Split-K plan: layers on the small pyramid levels have fewer tiles than SMs and a long, serial chunk walk per tile
-// (level 6: 32 tiles x up to 43 chunks, ~2 us per chunk from one issuing thread); k CTAs per tile take a k-th of the
-// chunks each.  Returns k (1 = no split).
-int conv3x3_umma_ksplit(int N, int Cin, int H, int W, int stride, int dil) {
+// Split-K plan.  Two cases, both about tiles being indivisible units of a persistent grid of 148 CTAs:
+//   small images (levels 5-6: 2 x tiles <= SMs, up to 43 chunks walked serially per tile at ~2 us per chunk): every tile is
+//     cut into k parts;
+//   a short last round (level 2: 896 tiles = 6 x 148 + 8 -- the 8 left-over tiles cost a 7th round, 13.5 % of the layer):
+//     only the tail tiles are cut, into as many parts as there are idle SMs, so the last round shrinks to 1/k of a tile.
+//     The tail is kept inside the last sample and aligned to whole tile rows, so the split region is a row range.
+// Returns k = 1 when nothing is split.
+static um::SplitK plan_split(int N, int Cin, int H, int W, int Cout, int stride, int dil, int grid_cap) {
   using namespace um;
   (void)dil;
-  if (!tuning().conv_splitk) return 1;
+  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr};
   const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1, nChunks = (Cin + 15) / 16;
-  const long long tiles = (long long)N * ((OW + MT - 1) / MT) * ((OH + R - 1) / R);
-  int k = (int)(kNumSMs / tiles);
-  if (k > nChunks / 3) k = nChunks / 3;   // at least 3 chunks per part
-  if (k > 8) k = 8;
-  if (tuning().conv_splitk > 1 && k > tuning().conv_splitk) k = tuning().conv_splitk;
-  return k < 2 ? 1 : k;
+  const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
+  const long long tiles = (long long)N * tilesX * tilesY;
+  sk.from = (int)tiles;
+  const int mode = tuning().conv_splitk;
+  if (!mode || tiles >= (1 << 30)) return sk;
+  const int sms = grid_cap > 0 && grid_cap < kNumSMs ? grid_cap : kNumSMs;
+  const int kcap = mode > 1 ? mode : 32;
+  if (2 * tiles <= sms) {                       // small image: split every tile
+    int k = (int)(sms / tiles);
+    if (k > nChunks / 3) k = nChunks / 3;       // at least 3 chunks per part
+    if (k > 8) k = 8;
+    if (k > kcap) k = kcap;
+    if (k >= 2) {
+      sk.k = k; sk.from = 0; sk.n_lo = 0; sk.y_lo = 0; sk.rh = OH;
+    }
+  } else if (tiles > sms) {                     // short last round: split the tail
+    const long long rounds = tiles / sms;
+    long long tail = tiles - rounds * sms;
+    tail = (tail + tilesX - 1) / tilesX * tilesX;                 // whole tile rows
+    int k = tail > 0 ? (int)(sms / tail) : 0;
+    if (k > nChunks / 2) k = nChunks / 2;       // at least 2 chunks per part
+    if (k > kcap) k = kcap;
+    if (tail > 0 && tail <= (long long)tilesX * tilesY && rounds <= 12 && k >= 2) {
+      sk.k = k; sk.from = (int)(tiles - tail); sk.n_lo = N - 1;
+      sk.y_lo = (int)((sk.from / tilesX) % tilesY) * R;
+      sk.rh = OH - sk.y_lo;
+    }
+  }
+  if (sk.k > 1) sk.part_stride = (long long)(N - sk.n_lo) * Cout * sk.rh * OW;
+  return sk;
 }
 
 long long conv3x3_umma_workspace_bytes(int N, int Cin, int H, int W, int Cout, int stride, int dil) {
-  const int k = conv3x3_umma_ksplit(N, Cin, H, W, stride, dil);
-  if (k < 2) return 0;
-  const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
-  return (long long)k * N * Cout * OH * OW * 4;
+  const um::SplitK sk = plan_split(N, Cin, H, W, Cout, stride, dil, tuning().conv_grid_cap);
+  return sk.k > 1 ? sk.k * sk.part_stride * 4 : 0;
 }
 
 // returns -1 when the shape does not fit this kernel (caller falls back to the mma.sync kernel)
@@ -649,45 +708,34 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   int cols = 32;
   while (cols < nacc * R * row_cols) cols *= 2;
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
-  // split-K when the caller lent a workspace (plain grids only)
-  int ksplit = 1;
+  // split-K when the caller lent a workspace (plain grids only): one launch covers the whole tiles (normal epilogue) and the
+  // parts of the split tiles (raw sums into the workspace), a second one reduces the split region
+  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr};
   if (ws != nullptr && ext == 0) {
-    ksplit = conv3x3_umma_ksplit(N, Cin, H, W, stride, dil);
-    if (ksplit > 1 && ws_bytes < (long long)ksplit * N * Cout * OH * OW * 4) ksplit = 1;
+    sk = plan_split(N, Cin, H, W, Cout, stride, dil, tuning().conv_grid_cap);
+    if (sk.k > 1 && ws_bytes < sk.k * sk.part_stride * 4) sk.k = 1;
+    sk.ws = ws;
   }
-  const long long part_stride = (long long)N * Cout * OH * OW;
-  const long long numTiles = (long long)N * tilesX * tilesY * ksplit;
+  const long long tiles = (long long)N * tilesX * tilesY;
+  if (sk.k <= 1) sk.from = (int)tiles;
+  const long long numTiles = sk.from + (tiles - sk.from) * sk.k;   // work items
   const int cap = tuning().conv_grid_cap > 0 ? tuning().conv_grid_cap : kNumSMs;
   const unsigned grid = (unsigned)(numTiles < cap ? numTiles : cap);
-  if (ksplit > 1) {
-    // pass 1: raw partial sums, plain NCHW into the workspace; pass 2: reduce + bias + activation (+ depth-to-space)
-#define MFN_UMMA_SPLIT(FOLD_, TPS_)                                                                                        \
-  conv3x3_umma_kernel<FOLD_, TPS_><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, nullptr, ws, (long long)Cout * OH * OW, Cin, \
-                                                                     H, W, OH, OW, Cout, CoutP, nChunks, 1.f, tilesX, tilesY,      \
-                                                                     (int)numTiles, stride, dil, 0, cols, nacc, 0, ksplit,          \
-                                                                     part_stride)
-    if (taps_per_stage(CoutP) == 9) MFN_UMMA_SPLIT(true, 9);
-    else if (taps_per_stage(CoutP) == 3) MFN_UMMA_SPLIT(true, 3);
-    else MFN_UMMA_SPLIT(false, 1);
-#undef MFN_UMMA_SPLIT
-    const int rc = check_launch("conv3x3_umma_kernel");
-    if (rc != 0) return rc;
-    const long long total = part_stride;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-    conv3x3_umma_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, ksplit, part_stride, bias, out, out_bs, N, Cout, OH, OW,
-                                                                slope, out_mode);
-    return check_launch("conv3x3_umma_reduce_kernel");
-  }
 #define MFN_UMMA_LAUNCH(FOLD_, TPS_)                                                                                       \
   conv3x3_umma_kernel<FOLD_, TPS_><<<grid, NTHREADS, sm.total, st>>>(x, x_bs, wpack, bias, out, out_bs, Cin, H, W, OH, OW, Cout,  \
                                                                      CoutP, nChunks, slope, tilesX, tilesY, (int)numTiles,      \
-                                                                     stride, dil, out_mode, cols, nacc, ext, 1, 0)
+                                                                     stride, dil, out_mode, cols, nacc, ext, sk)
   if (taps_per_stage(CoutP) == 9) MFN_UMMA_LAUNCH(true, 9);
   else if (taps_per_stage(CoutP) == 3) MFN_UMMA_LAUNCH(true, 3);
   else MFN_UMMA_LAUNCH(false, 1);
 #undef MFN_UMMA_LAUNCH
-  return check_launch("conv3x3_umma_kernel");
+  const int rc = check_launch("conv3x3_umma_kernel");
+  if (rc != 0 || sk.k <= 1) return rc;
+  const long long total = sk.part_stride;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  conv3x3_umma_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(sk, N - sk.n_lo, bias, out, out_bs, Cout, OH, OW, slope, out_mode);
+  return check_launch("conv3x3_umma_reduce_kernel");
 }
 
 }  // namespace mfn

@@ -54,7 +54,6 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
                         float slope, cudaStream_t st, int ext = 0, float* ws = nullptr, long long ws_bytes = 0);
 // split-K over the input-channel chunks for layers with fewer tiles than SMs: the plan (1 = none) and the fp32 workspace
 // the caller has to lend to conv3x3_umma_launch for it
-int conv3x3_umma_ksplit(int N, int Cin, int H, int W, int stride, int dil);
 long long conv3x3_umma_workspace_bytes(int N, int Cin, int H, int W, int Cout, int stride, int dil);
 
 }  // namespace mfn

@@ -513,6 +513,51 @@ def test_conv3x3_split_k_small_levels(N, Cin, Cout, H, W, mode):
     assert np.abs(outs[0] - outs[1]).max() <= 2e-5 * max(1.0, float(np.abs(ref).max()))
 
 
+@pytest.mark.parametrize("mode", ["nchw", "lin3", "d2s"])
+@pytest.mark.parametrize("N,Cin,Cout,H,W,cap", [(2, 100, 64, 14, 130, 12), (3, 70, 32, 9, 300, 20), (8, 64, 32, 112, 256, 0)])
+def test_conv3x3_split_k_last_round(N, Cin, Cout, H, W, cap, mode):
+    """Tiles are indivisible units of a persistent grid: when the last round is short (level 2: 896 tiles = 6 x 148 + 8) only
+    the left-over tiles are split over the channel chunks, the others run whole in the same launch; a second launch reduces
+    the tail's row range.  Small grids (conv_grid_cap) reproduce the situation cheaply; the last case is the real level-2
+    geometry.  Against float64 and against the unsplit kernel, for the three epilogues."""
+    rng = np.random.default_rng(59)
+    x = feat(rng, (N, Cin, H, W))
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    d2s = mode == "d2s"
+    F = Cout // 4 if d2s else Cout
+    b = (rng.standard_normal(F) * 0.1).astype(np.float32)
+    lin = 3 if mode == "lin3" else 0
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), None, padding=1)
+    if d2s:
+        ref = ref.reshape(N, 2, 2, F, H, W).permute(0, 3, 4, 1, 5, 2).reshape(N, F, 2 * H, 2 * W)
+    ref = ref + torch.from_numpy(b).double().view(1, F, 1, 1)
+    act = torch.nn.functional.leaky_relu(ref, 0.1)
+    if lin:
+        act[:, :lin] = ref[:, :lin]
+    ref = act.float().numpy()
+    packed = ops.conv3x3_pack(cu(w))
+    outs = []
+    _lib.set_tuning("conv_grid_cap", cap)
+    try:
+        ws_bytes = _lib.lib().mfn_conv3x3_workspace_bytes(N, Cin, H, W, Cout, 1, 1)
+        assert 0 < ws_bytes < 4 * N * Cout * H * W          # a tail region, not the whole tensor
+        for split in (1, 0):
+            _lib.set_tuning("conv_splitk", split)
+            out = torch.full((N, F + 3, (2 if d2s else 1) * H, (2 if d2s else 1) * W), float("nan"), device=DEV)
+            before = _lib.launch_count()
+            ops.conv3x3_slices(cu(x), 0, Cin, packed, cu(b), out, 2, Cout, 0.1, depth_to_space=d2s, linear_prefix=lin)
+            launches = _lib.launch_count() - before
+            assert launches == (2 if split else 1), launches
+            got = out[:, 2:2 + F].cpu().numpy()
+            assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max())), split
+            assert torch.isnan(out[:, :2]).all() and torch.isnan(out[:, 2 + F:]).all()
+            outs.append(got)
+    finally:
+        _lib.set_tuning("conv_splitk", 1)
+        _lib.set_tuning("conv_grid_cap", 0)
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-5 * max(1.0, float(np.abs(ref).max()))
+
+
 @pytest.mark.parametrize("cap", [1, 3])
 def test_conv3x3_persistent_tile_loop(cap):
     """The tcgen05 kernel is persistent: with the grid capped every CTA walks many tiles (stage rings wrap, barrier

@@ -6,8 +6,4 @@ echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --cpu-sample-
 import sys, json
 d = json.loads(sys.stdin.read())
 print({k: d[k] for k in ('value', 'ms_per_step', 'ms_per_step_eager')}, d['e2e']['value'])"
-echo "== bench no split"; MFN_TUNING=conv_splitk=0 timeout 600 python bench.py --steps 10 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read())
-print({k: d[k] for k in ('value', 'ms_per_step', 'ms_per_step_eager')}, d['e2e']['value'])"
-timeout 600 python tools/conv_profile.py > gpurun_out/conv_profile.txt 2>&1; head -3 gpurun_out/conv_profile.txt | cut -c1-150
+timeout 600 python tools/conv_profile.py > gpurun_out/conv_profile.txt 2>&1; head -14 gpurun_out/conv_profile.txt | cut -c1-150
