@@ -209,15 +209,39 @@ __global__ void __launch_bounds__(NT, 512 / NT)
 // ---------------------------------------------------------------------------------------------------------
 // Upsample(f) forward / backward (network/MaskFlownet.py:35-62)
 // ---------------------------------------------------------------------------------------------------------
+// One block row per output row (blockIdx.y = plane * OH + y, no 64-bit index arithmetic per element), four consecutive
+// output pixels per thread: row taps once, 16-byte stores when the row is aligned.
 __global__ void upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int H, int W,
                                     int f, float scale) {
   const int OH = H * f, OW = W * f;
-  const long long total = (long long)planes * OH * OW;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % OW), y = (int)((idx / OW) % OH);
-    const long long pl = idx / ((long long)OW * OH);
-    out[idx] = upsample_at(in + pl * H * W, H, W, f, y, x) * scale;
+  for (long long row = blockIdx.y; row < (long long)planes * OH; row += gridDim.y) {
+    const int pl = (int)(row / OH), y = (int)(row - (long long)pl * OH);
+    int y0, y1;
+    float wy;
+    upsample_taps(y, f, H, y0, y1, wy);
+    const float* r0 = in + ((size_t)pl * H + y0) * W;
+    const float* r1 = in + ((size_t)pl * H + y1) * W;
+    float* orow = out + (size_t)row * OW;
+    const bool vec = (OW & 3) == 0 && ((reinterpret_cast<size_t>(orow) & 15) == 0);
+    for (int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x); x4 < OW; x4 += 4 * gridDim.x * blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = min(x4 + k, OW - 1);
+        const int x0 = x / f, x1 = min(x0 + 1, W - 1);
+        const float wx = (float)(x - x0 * f) / (float)f;   // same rounding as upsample_taps
+        const float a = __ldg(r0 + x0), b = __ldg(r0 + x1), c = __ldg(r1 + x0), d = __ldg(r1 + x1);
+        const float top = a + (b - a) * wx, bot = c + (d - c) * wx;
+        v[k] = (top + (bot - top) * wy) * scale;
+      }
+      if (vec) {
+        *reinterpret_cast<float4*>(orow + x4) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (x4 + k < OW) orow[x4 + k] = v[k];
+      }
+    }
   }
 }
 
@@ -589,8 +613,10 @@ extern "C" int mfn_upsample_forward(const float* in, float* out, int planes, int
   using namespace mfn;
   MFN_REQUIRE(in && out, MFN_ERR_INVALID_ARG, "mfn_upsample_forward: null pointer");
   MFN_REQUIRE(planes > 0 && H > 0 && W > 0 && factor >= 1, MFN_ERR_INVALID_ARG, "mfn_upsample_forward: bad extent");
-  const long long total = (long long)planes * H * W * factor * factor;
-  upsample_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(in, out, planes, H, W, factor, scale);
+  const long long rows = (long long)planes * H * factor;
+  const int OW = W * factor, tpb = OW >= 1024 ? 256 : (OW >= 512 ? 128 : 64);
+  dim3 grid((unsigned)((OW + 4 * tpb - 1) / (4 * tpb)), (unsigned)(rows < 65535 ? rows : 65535));
+  upsample_fwd_kernel<<<grid, tpb, 0, as_stream(stream)>>>(in, out, planes, H, W, factor, scale);
   return check_launch("upsample_fwd_kernel");
 }
 

@@ -245,10 +245,11 @@ def test_warp_mask_backward(border, with_mask):
 # ------------------------------------------------------------------------------------------------------------
 # Upsample / image warp
 # ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 3, 5, 7), (1, 2, 28, 64), (3, 1, 9, 257)])
 @pytest.mark.parametrize("factor", [2, 4])
-def test_upsample_forward_backward(factor):
+def test_upsample_forward_backward(factor, shape):
     rng = np.random.default_rng(10)
-    u = rng.standard_normal((2, 3, 5, 7)).astype(np.float32)
+    u = rng.standard_normal(shape).astype(np.float32)
     ref = cref.upsample(u, factor)
     t = cu(u).requires_grad_()
     got = ops.upsample(t, factor)
