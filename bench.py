@@ -525,7 +525,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="fwd", choices=["fwd", "fwdbwd", "cascade", "train8"])
-    ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-steps", type=int, default=32)   # ~10 s of host work on a 16-thread box
     ap.add_argument("--sustain-seconds", type=float, default=3.0)
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 0)

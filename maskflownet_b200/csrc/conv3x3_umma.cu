@@ -135,7 +135,22 @@ struct SplitK {
   int k, from, n_lo, y_lo, rh;
   long long part_stride;
   float* ws;
+  // tile -> (n, ty, tx) without integer division: ceil(2^32 / (tilesX tilesY)) and ceil(2^32 / tilesX), or 0 when the
+  // products could overflow the exactness bound (then the kernel divides)
+  uint32_t magic_tp, magic_tx;
 };
+__device__ __forceinline__ void decode_tile(int tile, int tilesX, int tilesY, const SplitK& sk, int& tx, int& ty, int& n) {
+  if (sk.magic_tp) {
+    n = (int)__umulhi((uint32_t)tile, sk.magic_tp);
+    const int rem = tile - n * tilesX * tilesY;
+    ty = sk.magic_tx ? (int)__umulhi((uint32_t)rem, sk.magic_tx) : rem;   // magic_tx == 0: tilesX == 1
+    tx = rem - ty * tilesX;
+  } else {
+    tx = tile % tilesX;
+    ty = (tile / tilesX) % tilesY;
+    n = tile / (tilesX * tilesY);
+  }
+}
 struct Work {
   int tile, part, cb, ce;   // part < 0: a whole tile
 };
@@ -351,7 +366,8 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
     for (int work = blockIdx.x; work < numTiles; work += gridDim.x, ++j) {
       const Work wk = decode_work(work, sk, nChunks);
       const int tile = wk.tile;
-      const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+      int tx, ty, n;
+      decode_tile(tile, tilesX, tilesY, sk, tx, ty, n);
       // a part of a split tile: raw sums into its slot of the workspace region [n_lo.., all channels, y_lo.., OW]
       const bool partial = wk.part >= 0;
       const float* const bias = partial ? nullptr : bias_arg;
@@ -481,7 +497,8 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
         l_c = wk.cb;
         l_ce = wk.ce;
       }
-      const int tx = tl % tilesX, ty = (tl / tilesX) % tilesY, n = tl / (tilesX * tilesY);
+      int tx, ty, n;
+      decode_tile(tl, tilesX, tilesY, sk, tx, ty, n);
       // ext = 1: "full" convolution -- the output grid is the input grid extended by one pixel on every side
       // (OH = H + 2, OW = W + 2; output (y, x) sits at input position (y - 1, x - 1)); used by K3 through linearity
       l_x0 = tx * MT - (ext ? 1 : 0);
@@ -639,7 +656,7 @@ __global__ void conv3x3_umma_reduce_kernel(um::SplitK sk, int RN, const float* _
 static um::SplitK plan_split(int N, int Cin, int H, int W, int Cout, int stride, int dil, int grid_cap) {
   using namespace um;
   (void)dil;
-  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr};
+  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr, 0u, 0u};
   const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1, nChunks = (Cin + 15) / 16;
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
   const long long tiles = (long long)N * tilesX * tilesY;
@@ -663,7 +680,9 @@ static um::SplitK plan_split(int N, int Cin, int H, int W, int Cout, int stride,
     int k = tail > 0 ? (int)(sms / tail) : 0;
     if (k > nChunks / 2) k = nChunks / 2;       // at least 2 chunks per part
     if (k > kcap) k = kcap;
-    if (tail > 0 && tail <= (long long)tilesX * tilesY && rounds <= 12 && k >= 2) {
+    // measured (tools/conv_profile.py, level 2): pays for the long, tensor-bound layers (579 -> 128: 0.766 -> 0.685 ms,
+    // 387 -> 96, 259 -> 128); layers with few chunks or Cout <= 64 lose the gain to the second launch
+    if (tail > 0 && tail <= (long long)tilesX * tilesY && rounds <= 12 && k >= 2 && nChunks >= 16 && Cout > 64) {
       sk.k = k; sk.from = (int)(tiles - tail); sk.n_lo = N - 1;
       sk.y_lo = (int)((sk.from / tilesX) % tilesY) * R;
       sk.rh = OH - sk.y_lo;
@@ -710,7 +729,7 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
   // split-K when the caller lent a workspace (plain grids only): one launch covers the whole tiles (normal epilogue) and the
   // parts of the split tiles (raw sums into the workspace), a second one reduces the split region
-  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr};
+  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr, 0u, 0u};
   if (ws != nullptr && ext == 0) {
     sk = plan_split(N, Cin, H, W, Cout, stride, dil, tuning().conv_grid_cap);
     if (sk.k > 1 && ws_bytes < sk.k * sk.part_stride * 4) sk.k = 1;
@@ -718,6 +737,14 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   }
   const long long tiles = (long long)N * tilesX * tilesY;
   if (sk.k <= 1) sk.from = (int)tiles;
+  {
+    const unsigned long long tp = (unsigned long long)tilesX * tilesY;
+    if ((unsigned long long)tiles * tp < (1ull << 32) && tp * tilesX < (1ull << 32)) {   // q = umulhi(t, ceil(2^32 / d)) exact for t d < 2^32
+      sk.magic_tp = (uint32_t)(((1ull << 32) + tp - 1) / tp);
+      sk.magic_tx = tilesX == 1 ? 0u : (uint32_t)(((1ull << 32) + tilesX - 1) / tilesX);
+    }
+    if (tp == 1) sk.magic_tp = 0;          // ceil(2^32 / 1) does not fit 32 bits: the kernel divides
+  }
   const long long numTiles = sk.from + (tiles - sk.from) * sk.k;   // work items
   const int cap = tuning().conv_grid_cap > 0 ? tuning().conv_grid_cap : kNumSMs;
   const unsigned grid = (unsigned)(numTiles < cap ? numTiles : cap);

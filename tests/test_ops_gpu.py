@@ -515,12 +515,12 @@ def test_conv3x3_split_k_small_levels(N, Cin, Cout, H, W, mode):
 
 
 @pytest.mark.parametrize("mode", ["nchw", "lin3", "d2s"])
-@pytest.mark.parametrize("N,Cin,Cout,H,W,cap", [(2, 100, 64, 14, 130, 12), (3, 70, 32, 9, 300, 20), (8, 64, 32, 112, 256, 0)])
+@pytest.mark.parametrize("N,Cin,Cout,H,W,cap", [(2, 250, 96, 14, 130, 12), (3, 260, 68, 9, 300, 20), (3, 259, 96, 112, 256, 0)])
 def test_conv3x3_split_k_last_round(N, Cin, Cout, H, W, cap, mode):
     """Tiles are indivisible units of a persistent grid: when the last round is short (level 2: 896 tiles = 6 x 148 + 8) only
     the left-over tiles are split over the channel chunks, the others run whole in the same launch; a second launch reduces
-    the tail's row range.  Small grids (conv_grid_cap) reproduce the situation cheaply; the last case is the real level-2
-    geometry.  Against float64 and against the unsplit kernel, for the three epilogues."""
+    the tail's row range (long layers only: >= 16 chunks, Cout > 64).  Small grids (conv_grid_cap) reproduce the situation
+    cheaply; the last case is the level-2 geometry at batch 3 (336 tiles = 2 x 148 + 40).  Against float64 and against the unsplit kernel, for the three epilogues."""
     rng = np.random.default_rng(59)
     x = feat(rng, (N, Cin, H, W))
     w = (rng.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
