@@ -32,11 +32,11 @@ constexpr int R = 2;             // output rows per CTA
 constexpr int NTHREADS = 512;    // warps 0, 2: MMA issuers (warp 0 owns TMEM), warp 1: weight loader, warps 4..7: epilogue, rest: producers
 constexpr int NPROD = 9;         // producer warps: 3, 8..15
 constexpr int NISSUE = R;        // MMA-issuing threads: one per output row (lane 0 of warps 0 and 2)
-constexpr int MAX_AS = 4, MAX_WS = 16;
+constexpr int MAX_AS = 4, MAX_WS = 24;
 constexpr int BATCH = 4;         // producer items (32 entries x 8 channels) in flight per warp
 constexpr int MAX_ACC = 8;       // accumulator sets in TMEM (narrow layers: 2 rows x 32 columns each -- a deep ring hides the
                                  // commit -> epilogue -> acc_empty round trip, which is longer than such a tile's MMAs)
-constexpr int BAR_BYTES = 512;   // a_full/a_empty [MAX_AS], w_full/w_empty [MAX_WS], acc_full/acc_empty [MAX_ACC], TMEM pointer
+constexpr int BAR_BYTES = 1024;  // a_full/a_empty [MAX_AS], w_full/w_empty [MAX_WS], acc_full/acc_empty [MAX_ACC], TMEM pointer
 
 // Geometry of the converted input tile: `nslots` image rows of PW entries each.
 //   stride 1 (any dilation d): rows y0 - d .. y0 + R - 1 + d (or the 3R rows the taps touch when d >= R); entry p of a row is
@@ -138,6 +138,7 @@ struct SplitK {
   // tile -> (n, ty, tx) without integer division: ceil(2^32 / (tilesX tilesY)) and ceil(2^32 / tilesX), or 0 when the
   // products could overflow the exactness bound (then the kernel divides)
   uint32_t magic_tp, magic_tx;
+  int as_wide;   // input stages of the wide (single-tap weight stage) layers: 3 or 2 (smem_map)
 };
 __device__ __forceinline__ void decode_tile(int tile, int tilesX, int tilesY, const SplitK& sk, int& tx, int& ty, int& n) {
   if (sk.magic_tp) {
@@ -172,7 +173,7 @@ struct SmemMap {
   int a_lo, a_stage, w_tile, w_stage, w_off, bar_off, total, AS, WS;
 };
 // stage counts from the shared-memory budget: 3 input stages when that still leaves >= 8 weight stages, else 2
-__host__ __device__ inline SmemMap smem_map(int E, int CoutP) {
+__host__ __device__ inline SmemMap smem_map(int E, int CoutP, int as_wide = 3) {
   SmemMap m;
   m.a_lo = 2 * E * 16;              // hi image: two 8-channel planes of E entries
   m.a_stage = 2 * m.a_lo;           // hi + lo
@@ -183,8 +184,8 @@ __host__ __device__ inline SmemMap smem_map(int E, int CoutP) {
   // the weight ring deep (their weight stages are single taps) and take 3
   if (taps_per_stage(CoutP) > 1)
     m.AS = (4 * m.a_stage + 4 * m.w_stage <= budget) ? 4 : ((3 * m.a_stage + 3 * m.w_stage <= budget) ? 3 : 2);
-  else
-    m.AS = (3 * m.a_stage + 8 * m.w_stage <= budget) ? 3 : 2;
+  else   // as_wide (tuning "conv_as"): 2 trades an input stage for four more single-tap weight stages
+    m.AS = (as_wide >= 3 && 3 * m.a_stage + 8 * m.w_stage <= budget) ? 3 : 2;
   int ws = (budget - m.AS * m.a_stage) / m.w_stage;
   m.WS = ws > MAX_WS ? MAX_WS : ws;
   m.w_off = m.AS * m.a_stage;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(um::NTHREADS, 1)
   const int out_mode_k = out_mode_arg & 0xff, lin_prefix_k = out_mode_arg >> 8;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nslots = n_slots(stride, dil), PW = row_pitch(stride, dil), E = nslots * PW;
-  const SmemMap sm = smem_map(E, CoutP);
+  const SmemMap sm = smem_map(E, CoutP, sk.as_wide);
   const int AS = sm.AS, WS = sm.WS;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + sm.bar_off;
@@ -656,7 +657,7 @@ __global__ void conv3x3_umma_reduce_kernel(um::SplitK sk, int RN, const float* _
 static um::SplitK plan_split(int N, int Cin, int H, int W, int Cout, int stride, int dil, int grid_cap) {
   using namespace um;
   (void)dil;
-  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr, 0u, 0u};
+  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr, 0u, 0u, 3};
   const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1, nChunks = (Cin + 15) / 16;
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
   const long long tiles = (long long)N * tilesX * tilesY;
@@ -707,7 +708,8 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   if ((out_mode >> 8) != 0 && (out_mode & 0xff) != 0) return -1;   // linear prefix only with plain NCHW output
   const int CoutP = um::cout_pad(Cout), nChunks = (Cin + 15) / 16;
   const int E = n_slots(stride, dil) * row_pitch(stride, dil);
-  const SmemMap sm = smem_map(E, CoutP);
+  const int as_wide = tuning().conv_as == 2 ? 2 : 3;
+  const SmemMap sm = smem_map(E, CoutP, as_wide);
   if (sm.WS < 2 || E * 16 > 0x3FFF * 16) return -1;
   if ((long long)H * W >= (1LL << 27)) return -1;   // the producers address a 16-plane chunk with 32-bit element offsets
   const int grow = ext == 2 ? 8 : 2 * ext;   // ext 1: grid + 1 pixel per side; ext 2: + the six band rows / columns too
@@ -729,13 +731,14 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   const int tilesX = (OW + MT - 1) / MT, tilesY = (OH + R - 1) / R;
   // split-K when the caller lent a workspace (plain grids only): one launch covers the whole tiles (normal epilogue) and the
   // parts of the split tiles (raw sums into the workspace), a second one reduces the split region
-  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr, 0u, 0u};
+  SplitK sk = {1, 0, 0, 0, 0, 0, nullptr, 0u, 0u, 3};
   if (ws != nullptr && ext == 0) {
     sk = plan_split(N, Cin, H, W, Cout, stride, dil, tuning().conv_grid_cap);
     if (sk.k > 1 && ws_bytes < sk.k * sk.part_stride * 4) sk.k = 1;
     sk.ws = ws;
   }
   const long long tiles = (long long)N * tilesX * tilesY;
+  sk.as_wide = as_wide;
   if (sk.k <= 1) sk.from = (int)tiles;
   {
     const unsigned long long tp = (unsigned long long)tilesX * tilesY;

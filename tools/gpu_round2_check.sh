@@ -1,8 +1,11 @@
 #!/bin/bash
-# round-2 GPU batch (edited per batch): final measurements
+# round-2 GPU batch (edited per batch)
 mkdir -p gpurun_out
-echo "== conv tests"; timeout 900 python -m pytest tests/test_ops_gpu.py -q -m gpu -x -k "conv" 2>&1 | tail -3
-echo "== default bench"; ( time timeout 900 python bench.py ) 2>&1 | tail -6 | tee gpurun_out/r02_bench_default.txt | cut -c1-300
-echo "== reference arm"; ( time timeout 900 python bench.py --impl reference --steps 3 --warmup 1 ) 2>&1 | tail -5 | tee gpurun_out/r02_bench_reference.txt | cut -c1-200
-echo "== cascade"; timeout 600 python bench.py --config cascade --cpu-sample-steps 0 2>&1 | tail -1 | tee gpurun_out/r02_bench_cascade_1gpu.json | cut -c1-300
-echo "== fwdbwd"; timeout 600 python bench.py --config fwdbwd --cpu-sample-steps 0 2>&1 | tail -1 | tee gpurun_out/r02_bench_fwdbwd_1gpu.json | cut -c1-300
+echo "== conv tests (conv_as=2)"; MFN_TUNING=conv_as=2 timeout 900 python -m pytest tests/test_ops_gpu.py -q -m gpu -x -k "conv" 2>&1 | tail -3
+for t in "" "conv_as=2"; do
+echo "== bench [$t]"; MFN_TUNING=$t timeout 600 python bench.py --steps 10 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+print({k: d[k] for k in ('value', 'ms_per_step', 'ms_per_step_eager')}, d['e2e']['value'])"
+done
+echo "== wide convs"; for t in "" "conv_as=2"; do MFN_TUNING=$t timeout 300 python tools/dev_conv_narrow.py 2>&1 | tail -2 | cut -c1-130; done
