@@ -69,7 +69,13 @@ __host__ __device__ inline int cout_pad(int cout) { return cout <= 16 ? 16 : (co
 // N: profiles/r01_ubench_tcgen05_mma_issue.txt), so they fold the hi / lo weight images into ONE operand of 2N rows:
 //   D[:, 0:2N] += A_hi x [B_hi ; B_lo]      (N' = 2N)        D[:, 0:N] += A_lo x B_hi
 // two instructions per product instead of three; the epilogue adds the two column blocks.
-__host__ __device__ inline bool fold_hi_lo(int CoutP) { return CoutP <= 64; }
+// Folding the long wide layers too (65 <= N <= 128, >= 16 chunks: one accumulator set of 2 x 2N = 512 TMEM columns,
+// 100 instead of 120 B/clk of shared-memory operand reads) was measured neutral (579 -> 128: 0.685 -> 0.667 ms, 259 -> 128:
+// 0.330 -> 0.349 ms; step 7.09 -> 7.07 ms) and is not used; the <true, 1> instance stays compiled for the experiment.
+__host__ __device__ inline bool fold_hi_lo(int CoutP, int nChunks) {
+  (void)nChunks;
+  return CoutP <= 64;
+}
 // Taps per weight-ring stage (compile-time variants of the kernel).  Both rings are bound by their ROUND-TRIP latency
 // (commit -> mbarrier -> waiting thread wakes -> copy / conversion -> mbarrier -> issuer wakes: ~2 us measured), not by
 // bandwidth: a ring of S stages delivers S stages per round trip.  Narrow layers, whose MMAs per tap are short, therefore
@@ -215,7 +221,7 @@ __global__ void conv3x3_pack_umma_kernel(const float* __restrict__ w, unsigned c
     c3::split_pair(a, b, hi, lo);
     const int wt = 64 * CoutP;
     unsigned char* tile = packed + ((size_t)c * 9 + tap) * wt;
-    if (um::fold_hi_lo(CoutP)) {   // [8-channel plane][hi rows | lo rows][16 B]
+    if (um::fold_hi_lo(CoutP, nChunks16)) {   // [8-channel plane][hi rows | lo rows][16 B]
       const int off = (j >> 2) * (2 * CoutP * 16) + f * 16 + (j & 3) * 4;
       *reinterpret_cast<uint32_t*>(tile + off) = hi;
       *reinterpret_cast<uint32_t*>(tile + CoutP * 16 + off) = lo;
@@ -714,14 +720,16 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
   if ((long long)H * W >= (1LL << 27)) return -1;   // the producers address a 16-plane chunk with 32-bit element offsets
   const int grow = ext == 2 ? 8 : 2 * ext;   // ext 1: grid + 1 pixel per side; ext 2: + the six band rows / columns too
   const int OH = stride == 2 ? (H - 1) / 2 + 1 : H + grow, OW = stride == 2 ? (W - 1) / 2 + 1 : W + grow;
-  static SmemOptIn opt0, opt3, opt9;
+  static SmemOptIn opt0, opt1, opt3, opt9;
   {
     cudaError_t e = ensure_dyn_smem(conv3x3_umma_kernel<false, 1>, sm.total, opt0);
+    if (e == cudaSuccess) e = ensure_dyn_smem(conv3x3_umma_kernel<true, 1>, sm.total, opt1);
     if (e == cudaSuccess) e = ensure_dyn_smem(conv3x3_umma_kernel<true, 3>, sm.total, opt3);
     if (e == cudaSuccess) e = ensure_dyn_smem(conv3x3_umma_kernel<true, 9>, sm.total, opt9);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(conv3x3_umma_kernel): %s", cudaGetErrorString(e));
   }
-  const int row_cols = fold_hi_lo(CoutP) ? 2 * CoutP : CoutP;   // TMEM columns per output row
+  const bool fold = fold_hi_lo(CoutP, nChunks);
+  const int row_cols = fold ? 2 * CoutP : CoutP;   // TMEM columns per output row
   // accumulator ring: as many sets as fit the 512 TMEM columns (2 at N = 128, 8 for the narrow layers), or the tuning cap
   int nacc = 512 / (R * row_cols);
   nacc = nacc < 1 ? 1 : (nacc > MAX_ACC ? MAX_ACC : nacc);
@@ -757,6 +765,7 @@ int conv3x3_umma_launch(const float* x, long long x_bs, const unsigned char* wpa
                                                                      stride, dil, out_mode, cols, nacc, ext, sk)
   if (taps_per_stage(CoutP) == 9) MFN_UMMA_LAUNCH(true, 9);
   else if (taps_per_stage(CoutP) == 3) MFN_UMMA_LAUNCH(true, 3);
+  else if (fold) MFN_UMMA_LAUNCH(true, 1);
   else MFN_UMMA_LAUNCH(false, 1);
 #undef MFN_UMMA_LAUNCH
   const int rc = check_launch("conv3x3_umma_kernel");

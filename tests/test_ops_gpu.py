@@ -410,7 +410,8 @@ def test_conv3x3_dilated(dil):
 @pytest.mark.parametrize("umma", [1, 0])
 @pytest.mark.parametrize("N,Cin,Cout,H,W,dil", [(1, 16, 32, 4, 128, 1), (1, 32, 64, 5, 130, 1), (1, 64, 96, 9, 256, 1),
                                                 (2, 131, 128, 12, 40, 1), (1, 40, 96, 21, 45, 2), (1, 40, 64, 21, 45, 16),
-                                                (1, 128, 128, 30, 200, 8), (1, 20, 2, 9, 140, 1), (1, 33, 16, 6, 70, 1)])
+                                                (1, 128, 128, 30, 200, 8), (1, 20, 2, 9, 140, 1), (1, 33, 16, 6, 70, 1),
+                                                (1, 300, 128, 9, 140, 1), (2, 260, 96, 7, 40, 2)])
 def test_conv3x3_tcgen05_and_mma_sync_agree_with_fp64(N, Cin, Cout, H, W, dil, umma):
     """Both kernels behind mfn_conv3x3_forward (tcgen05/TMEM and mma.sync) against a float64 convolution, incl. tiles that
     straddle the 128-pixel M tile, the image border, channel-chunk padding and N padding."""
