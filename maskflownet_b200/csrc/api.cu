@@ -50,6 +50,7 @@ extern "C" int mfn_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "corr_disable_ring")) mfn::tuning().corr_disable_ring = value;
   else if (!strcmp(key, "warp_lin")) mfn::tuning().warp_lin = value;
   else if (!strcmp(key, "corr_rb")) mfn::tuning().corr_rb = value;
+  else if (!strcmp(key, "warp_lin_fch")) mfn::tuning().warp_lin_fch = value;
   else if (!strcmp(key, "conv_as")) mfn::tuning().conv_as = value;
   else if (!strcmp(key, "conv_splitk")) mfn::tuning().conv_splitk = value;
   else if (!strcmp(key, "conv_nacc")) mfn::tuning().conv_nacc = value;

@@ -21,6 +21,7 @@ struct Tuning {
   int conv_umma_min_w = 1;    // narrower images stay on the mma.sync kernel (a 128-pixel M tile would be mostly padding)
   int corr_ring_th = 8;       // tile height of the strip-marching kernel: 4 (8 warps, 2 CTAs/SM) or 8 (16 warps, 1 CTA/SM)
   int corr_rb = 1;            // 1: C > 32 correlations run on the row-block kernel (corr_rb.cu); 2: also C <= 32 when the TMA kernel declines; 0: chunked tile kernel
+  int warp_lin_fch = 0;       // > 0: channels per thread of warp_lin_kernel (a multiple of 8; default: 16 / 32 / 64 by level size)
   int conv_as = 0;            // 2: wide tcgen05 layers keep 2 input stages (more weight stages); default 3
   int conv_splitk = 1;        // 0: never split K; 1: plan decides (<= 8 parts); k > 1: cap on the number of parts
   int conv_nacc = 0;          // > 0: cap on the tcgen05 convolution's TMEM accumulator ring (default: as many as fit, <= 8)

@@ -58,25 +58,36 @@ __device__ __forceinline__ Band bands(int p, float d, int n) {
 //   cols W+4-j / W+7-j             ... of the first / last image column with weight column j               (Rcol)
 //   their intersections            W_ij . x[corner]                                                         (T)
 // One thread per (pixel, chunk of FCH output channels): all accesses coalesced along x.
-constexpr int FCH = 16;
+constexpr int FCH = 16;   // smallest channel chunk (a multiple of the 8-channel load batch); the launch picks 16 / 32 / 64 per thread
 template <int BORDER>
 __global__ void __launch_bounds__(256)
     warp_lin_kernel(const float* __restrict__ Yall, const float* __restrict__ flow_c, const float* __restrict__ mask_c,
                     const float* __restrict__ bias, const float* __restrict__ tradeoff, float* __restrict__ out,
                     float* __restrict__ flow_up_out, float* __restrict__ mask_up_out, int N, int H, int W, int F, int up,
-                    float flow_scale, float level_stride, float slope, int grow) {
+                    float flow_scale, float level_stride, float slope, int grow, int fch) {
   const long long total = (long long)N * H * W;
   const size_t plane = (size_t)H * W;
   const int WA = W + grow, HA = H + grow;
   const size_t aplane = (size_t)HA * WA;
-  const int f0 = blockIdx.y * FCH, f1 = min(F, f0 + FCH);
+  // per-pixel set-up (flow / mask up-sampling, corner weights, band entries) is ~40 % of a 16-channel thread's
+  // instructions: big levels take more channels per thread (fch), small levels keep 16 for the sake of parallelism
+  const int f0 = blockIdx.y * fch, f1 = min(F, f0 + fch);
+  const int Hc = H / up, Wc = W / up;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-    const int xq = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / plane);
-    const int Hc = H / up, Wc = W / up;
+    const unsigned pu = (unsigned)p;                   // total < 2^31 (checked by the host): 32-bit index arithmetic
+    const int n = (int)(pu / (unsigned)plane), rem = (int)(pu - (unsigned)n * (unsigned)plane);
+    const int y = rem / W, xq = rem - y * W;
     const float* fc = flow_c + (size_t)n * 2 * Hc * Wc;
-    const float fy = upsample_at(fc, Hc, Wc, up, y, xq);
-    const float fx = upsample_at(fc + (size_t)Hc * Wc, Hc, Wc, up, y, xq);
-    const float mask_v = mask_c ? upsample_at(mask_c + (size_t)n * Hc * Wc, Hc, Wc, up, y, xq) : 0.f;
+    float fy, fx, mask_v;
+    if (up == 2) {                                     // the network's Upsample(2): constant-folded taps
+      fy = upsample_at(fc, Hc, Wc, 2, y, xq);
+      fx = upsample_at(fc + (size_t)Hc * Wc, Hc, Wc, 2, y, xq);
+      mask_v = mask_c ? upsample_at(mask_c + (size_t)n * Hc * Wc, Hc, Wc, 2, y, xq) : 0.f;
+    } else {
+      fy = upsample_at(fc, Hc, Wc, up, y, xq);
+      fx = upsample_at(fc + (size_t)Hc * Wc, Hc, Wc, up, y, xq);
+      mask_v = mask_c ? upsample_at(mask_c + (size_t)n * Hc * Wc, Hc, Wc, up, y, xq) : 0.f;
+    }
     const size_t pix = (size_t)y * W + xq;
     if (blockIdx.y == 0) {
       if (flow_up_out) {
@@ -197,15 +208,20 @@ int launch_warp_lin(const float* x, const float* flow_c, const float* mask_c, co
                                (long long)F * (H + grow) * (W + grow), N, C, H, W, F, 1, 1, MFN_CONV_OUT_NCHW, 1.0f, st, ext);
   if (rc) return rc;
   const long long total = (long long)N * H * W;
+  if (total >= (1LL << 31)) return -1;
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 8) blocks = 148LL * 8;
-  const dim3 grid((unsigned)blocks, (unsigned)((F + FCH - 1) / FCH));
+  // channels per thread: doubled while at least one resident wave of threads (148 SMs x 512) remains
+  int fch = FCH;
+  while (fch < 64 && fch < F && total * ((F + 2 * fch - 1) / (2 * fch)) >= 148LL * 512) fch *= 2;
+  if (tuning().warp_lin_fch > 0) fch = tuning().warp_lin_fch;
+  const dim3 grid((unsigned)blocks, (unsigned)((F + fch - 1) / fch));
   if (border_mode == MFN_BORDER_MXNET15)
     warp_lin_kernel<MFN_BORDER_MXNET15><<<grid, 256, 0, st>>>(Yall, flow_c, mask_c, bias, tradeoff, out, fup, mup, N, H, W, F, up,
-                                                             fs, ls, slope, grow);
+                                                             fs, ls, slope, grow, fch);
   else
     warp_lin_kernel<MFN_BORDER_ZERO_CORNER><<<grid, 256, 0, st>>>(Yall, flow_c, mask_c, bias, tradeoff, out, fup, mup, N, H, W, F,
-                                                                 up, fs, ls, slope, grow);
+                                                                 up, fs, ls, slope, grow, fch);
   return check_launch("warp_lin_kernel");
 }
 
