@@ -272,6 +272,41 @@ MFN_API int mfn_preprocess_forward(const void* img1, const void* img2, int is_ui
 MFN_API int mfn_postprocess_forward(const float* pred, float* out, int N, int channels, int Hq, int Wq, int H, int W,
                                     int flip_channels, int is_flow, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * GPU-side training augmentation: /root/reference/augmentation.py:168-339, constructed in
+ * main.py:386-419, applied in network/pipeline.py:100-102 (`/ 255`, geo_aug, color_aug).  The random draws and the small
+ * per-sample matrices derived from them are host logic (maskflownet_b200/augment.py); the kernels take the result as a
+ * parameter block and are deterministic.
+ *
+ * mfn_geometry_augment_forward replaces GeometryAugmentation.hybrid_forward (augmentation.py:278-339) in ONE launch.
+ *   img1 / img2 (N,3,H,W) and mask (N,1,H,W), or (N,1,1,1) when mask_broadcast (train_batch's default mask, pipeline.py:93-94):
+ *   uint8 when is_uint8 (read as value / 255, pipeline.py:100) else float32; flow (N,2,H,W) float32, channel 0 = x.
+ *   params (N,22) float32 per sample:
+ *     [0:6]   affine_params  (:291-293)            the first image's 2x3 affine map, row-major, in normalised coordinates
+ *     [6:12]  affine_2       (:305)                = affine_params . relative transform
+ *     [12:14] rel_translation (:302), zeros when the block has none: added to the second grid (:323-324) and, times
+ *             ((W-1)/2, (H-1)/2), subtracted from the flow (:303-307)
+ *     [14:18] inverse_2      (:326) 2x2 applied to the sampled flow    [18:22] factor (:337) 2x2 applied to the identity grid
+ *   outputs on the (TH,TW) target grid: out_img1 / out_img2 (N,3,TH,TW), out_flow (N,2,TH,TW), out_mask (N,1,TH,TW).
+ *   GridGenerator('affine') and BilinearSampler semantics: MXNet's (grid x = -1 + j*2/(TW-1); zero weight for taps outside).
+ * mfn_color_augment_forward replaces ColorAugmentation.hybrid_forward (augmentation.py:182-227) for both images in two
+ *   launches.  img1 / img2 / out1 / out2 (N,3,H,W) float32; params (N,26) per sample:
+ *     [0:9] sh_matrix (:198-200)  [9:12] contrast * channel (:218)  [12:15] channel  [15] brightness (:221)
+ *     [16] exp(gamma) (:224; used when has_gamma)  [17:26] spin_matrix (:206-208), the identity without eigen_aug.
+ *   noise1 / noise2: (N,3,H,W) standard-normal tensors (the reference's F.random.normal, :214), or both null: then, when
+ *   noise_sigma != 0, the kernels generate the noise themselves (Philox4x32-10 keyed by `seed`, counter = pixel index).
+ *   workspace: mfn_color_augment_workspace_bytes(N) bytes of caller-owned scratch (per-slice partial sums; no atomics,
+ *   so the result is bit-reproducible).
+ * ------------------------------------------------------------------------------------------------- */
+MFN_API int mfn_geometry_augment_forward(const void* img1, const void* img2, int is_uint8, const float* flow, const void* mask,
+                                         int mask_broadcast, const float* params, float* out_img1, float* out_img2,
+                                         float* out_flow, float* out_mask, int N, int H, int W, int TH, int TW, void* stream);
+MFN_API long long mfn_color_augment_workspace_bytes(int N);
+MFN_API int mfn_color_augment_forward(const float* img1, const float* img2, const float* params, const float* noise1,
+                                      const float* noise2, float noise_sigma, long long seed, float* out1, float* out2,
+                                      void* workspace, long long workspace_bytes, int N, int H, int W, int has_gamma,
+                                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,8 @@ SIGNATURES = {
     "mfn_image_warp_concat_forward": [_f] * 6 + [_i] * 4 + [_fl, _f],
     "mfn_preprocess_forward": [_f, _f, _i, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "mfn_postprocess_forward": [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _f],
+    "mfn_geometry_augment_forward": [_f, _f, _i, _f, _f, _i, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f],
+    "mfn_color_augment_forward": [_f, _f, _f, _f, _f, _fl, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _f],
     "mfn_set_tuning": [ctypes.c_char_p, _i],
     "mfn_conv3x3_pack_weights": [_f, _f, _i, _i, _f],
     "mfn_conv3x3_forward": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _fl, _f],
@@ -72,6 +74,8 @@ def lib() -> ctypes.CDLL:
         L.mfn_conv3x3_packed_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
         L.mfn_conv3x3_workspace_bytes.restype = ctypes.c_longlong
         L.mfn_conv3x3_workspace_bytes.argtypes = [ctypes.c_int] * 7
+        L.mfn_color_augment_workspace_bytes.restype = ctypes.c_longlong
+        L.mfn_color_augment_workspace_bytes.argtypes = [ctypes.c_int]
         L.mfn_warp_resample_workspace_bytes.restype = ctypes.c_longlong
         L.mfn_warp_resample_workspace_bytes.argtypes = [ctypes.c_int] * 4
         for name, argtypes in SIGNATURES.items():
@@ -82,6 +86,9 @@ def lib() -> ctypes.CDLL:
         # experiment hook: MFN_TUNING="key=value,key=value" applies mfn_set_tuning at load time
         for item in filter(None, os.environ.get("MFN_TUNING", "").split(",")):
             key, _, val = item.partition("=")
+            if key.strip() == "corr_dbg":
+                # the phase-ablation switches produce INVALID results: tools set them through set_tuning(), never the environment
+                raise MaskflowError("MFN_TUNING: corr_dbg is a profiling switch (results invalid); set it from a tool, not the environment")
             if L.mfn_set_tuning(key.strip().encode(), int(val)):
                 raise MaskflowError(f"MFN_TUNING: {L.mfn_last_error().decode()}")
     return _lib

@@ -1,0 +1,302 @@
+"""Row N4: GPU-side training augmentation, /root/reference/augmentation.py:168-339.
+
+CPU part (`-m "not gpu"`): the numpy restatement (oracle/augment_ref.py) against the fixture produced by the reference's own
+augmentation.py (tests/golden/make_golden_aug.py); the product's host logic (draws -> parameter blocks) against the oracle;
+and the kernel SOURCE of csrc/augment.cu compiled for the host (tests/host_emu/) against the oracle.
+GPU part (`-m gpu`): mfn_geometry_augment_forward / mfn_color_augment_forward through the C ABI against the oracle.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment_ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = os.path.join(HERE, "golden", "aug_ref_graph.npz")
+GEO_NAMES = ["rotation", "aspect_ratio", "scale", "tx_unit", "tx_range", "ty_unit", "ty_range", "rel_rotation", "rel_scale",
+             "rel_translation"]
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return dict(np.load(FIX))
+
+
+def geo_draws(fx, prefix="geo"):
+    return {k: fx[f"{prefix}_draw_{k}"] for k in GEO_NAMES}
+
+
+def col_draws(fx, prefix):
+    return {k[len(prefix) + 6:]: v for k, v in fx.items() if k.startswith(prefix + "_draw_")}
+
+
+def shapes(fx):
+    return tuple(int(v) for v in fx["orig_shape"]), tuple(int(v) for v in fx["target_shape"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle vs the reference's own graph
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prefix", ["geo", "geob"])
+def test_oracle_geometry_matches_reference_graph(fx, prefix):
+    orig, target = shapes(fx)
+    P = augment_ref.geometry_params(geo_draws(fx, prefix), orig, target)
+    mask = fx["mask"] if prefix == "geo" else np.ones((fx["img1"].shape[0], 1, 1, 1), np.float32)
+    out = augment_ref.geometry_augment(fx["img1"], fx["img2"], fx["flow"], mask, P, target)
+    for name, got in zip(("img1", "img2", "flow", "mask"), out):
+        ref = fx[f"{prefix}_{name}"]
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < (2e-4 if name == "flow" else 2e-5), name
+    assert np.abs(out[2]).max() > 1.0 and (prefix == "geob" or 0 < out[3].mean() < 1)
+
+
+def test_oracle_color_matches_reference_graph(fx):
+    d = col_draws(fx, "col")
+    P = augment_ref.color_params(d, gamma=True, eigen=False)
+    sigma = float(d["noise_sigma"][0])
+    assert sigma > 0
+    for k, img in (("1", fx["geo_img1"]), ("2", fx["geo_img2"])):
+        got = augment_ref.color_augment_one(img, P, noise=d["noise" + k], noise_sigma=sigma)
+        assert np.abs(got - fx["col_img" + k]).max() < 2e-5
+    e = col_draws(fx, "eig")
+    Pe = augment_ref.color_params(e, gamma=False, eigen=True)
+    for k, img in (("1", fx["geo_img1"]), ("2", fx["geo_img2"])):
+        got = augment_ref.color_augment_one(img, Pe)
+        assert np.abs(got - fx["eig_img" + k]).max() < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# product host logic (draws -> parameter blocks)
+# ---------------------------------------------------------------------------------------------------------------
+def make_geo(orig, target, N, seed=None):
+    from maskflownet_b200 import augment
+    return augment.GeometryAugmentation(angle_range=(-17, 17), zoom_range=(0.5, 1 / 0.9), aspect_range=(0.9, 1 / 0.9),
+                                        translation_range=0.1, target_shape=target, orig_shape=orig, batch_size=N,
+                                        relative_angle=0.25, relative_scale=(0.96, 1 / 0.96), relative_translation=0.25, seed=seed)
+
+
+def test_host_geometry_params_match_oracle(fx):
+    orig, target = shapes(fx)
+    geo = make_geo(orig, target, 3)
+    for prefix in ("geo", "geob"):
+        d = geo_draws(fx, prefix)
+        got = geo.params({k: torch.from_numpy(v) for k, v in d.items()}).numpy()
+        want = augment_ref.geometry_params(d, orig, target)
+        assert got.shape == want.shape == (3, 22)
+        assert np.abs(got - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+
+
+def test_host_color_params_match_oracle(fx):
+    from maskflownet_b200 import augment
+    _, target = shapes(fx)
+    kitti = augment.ColorAugmentation(contrast_range=(-0.2, 0.4), brightness_sigma=0.05, channel_range=(0.9, 1.2), batch_size=3,
+                                      shape=target, noise_range=(0, 0.02), saturation=0.25, hue=0.1, gamma_range=(-0.5, 0.5))
+    d = col_draws(fx, "col")
+    got = kitti.params({k: torch.from_numpy(np.asarray(v)) for k, v in d.items() if not k.startswith("noise") or k == "noise_sigma"})
+    assert np.abs(got.numpy() - augment_ref.color_params(d, gamma=True)).max() < 1e-6
+    sintel = augment.ColorAugmentation(contrast_range=(-0.4, 0.8), brightness_sigma=0.1, channel_range=(0.8, 1.4), batch_size=3,
+                                       shape=target, noise_range=(0, 0), saturation=0.5, hue=0.5, eigen_aug=True)
+    e = col_draws(fx, "eig")
+    got = sintel.params({k: torch.from_numpy(np.asarray(v)) for k, v in e.items()})
+    assert np.abs(got.numpy() - augment_ref.color_params(e, eigen=True)).max() < 1e-6
+
+
+def test_host_sampling_ranges_and_determinism():
+    geo = make_geo((384, 512), (320, 448), 8, seed=11)
+    d = geo.sample()
+    assert list(d) == GEO_NAMES and d["rel_translation"].shape == (8, 2)
+    assert (d["rotation"].abs() <= 17 / 180 * np.pi + 1e-6).all() and (d["scale"] >= 0.5).all() and (d["scale"] <= 1 / 0.9 + 1e-6).all()
+    assert (d["rel_translation"].abs() <= 0.05 + 1e-6).all()      # 0.25 * (2 * 0.1)
+    P = geo.params(d)
+    assert P.shape == (8, 22) and torch.isfinite(P).all()
+    assert torch.equal(make_geo((384, 512), (320, 448), 8, seed=11).sample()["scale"], d["scale"])
+    with pytest.raises(Exception):
+        from maskflownet_b200 import augment
+        augment.GeometryAugmentation((-1, 1), (1, 1), 0.1, (8, 8), (8, 8), 1)     # the reference has no non-relative path
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the kernel source compiled for the host (no GPU in the development container)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libaugment_emu.so")
+    src = os.path.join(HERE, "host_emu", "augment_emu.cpp")
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(HERE, "host_emu"), "-o", out, src],
+                   check=True)
+    return ctypes.CDLL(out)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def emu_geometry(emu, img1, img2, flow, mask, P, target):
+    N, _, H, W = img1.shape
+    TH, TW = target
+    o1, o2 = np.zeros((N, 3, TH, TW), np.float32), np.zeros((N, 3, TH, TW), np.float32)
+    of, om = np.zeros((N, 2, TH, TW), np.float32), np.zeros((N, 1, TH, TW), np.float32)
+    arrs = [np.ascontiguousarray(a) for a in (img1, img2, flow, mask, P)]
+    emu.emu_geometry_augment(_ptr(arrs[0]), _ptr(arrs[1]), int(img1.dtype == np.uint8), _ptr(arrs[2]), _ptr(arrs[3]),
+                             int(mask.shape[2:] == (1, 1) and (H, W) != (1, 1)), _ptr(arrs[4]), _ptr(o1), _ptr(o2), _ptr(of),
+                             _ptr(om), N, H, W, TH, TW)
+    return o1, o2, of, om
+
+
+def geometry_case(seed, N, orig, target, uint8, bcast):
+    rng = np.random.default_rng(seed)
+    H, W = orig
+    if uint8:
+        img1 = rng.integers(0, 256, (N, 3, H, W), dtype=np.uint8)
+        img2 = rng.integers(0, 256, (N, 3, H, W), dtype=np.uint8)
+        mask = np.full((N, 1, 1, 1), 255, np.uint8) if bcast else (rng.random((N, 1, H, W)) > 0.2).astype(np.uint8) * 255
+    else:
+        img1, img2 = rng.random((N, 3, H, W), dtype=np.float32), rng.random((N, 3, H, W), dtype=np.float32)
+        mask = np.ones((N, 1, 1, 1), np.float32) if bcast else (rng.random((N, 1, H, W)) > 0.2).astype(np.float32)
+    flow = (rng.standard_normal((N, 2, H, W)) * 4).astype(np.float32)
+    geo = make_geo(orig, target, N, seed=seed)
+    d = geo.sample()
+    P = geo.params(d).numpy()
+    P[0, 12:14] += np.float32(0.7)      # sample 0: a relative translation that pushes the second grid out of the image (zero padding)
+    return img1, img2, flow, mask, P, geo, d
+
+
+def oracle_geometry(img1, img2, flow, mask, P, target):
+    if img1.dtype == np.uint8:
+        img1, img2, mask = (a.astype(np.float32) / np.float32(255) for a in (img1, img2, mask))
+    return augment_ref.geometry_augment(img1, img2, flow, mask, P, target)
+
+
+def check_geometry(got, want, tag=""):
+    for name, a, b in zip(("img1", "img2", "flow", "mask"), got, want):
+        tol = 1e-5 if name != "flow" else 1e-5 * max(1.0, float(np.abs(b).max()))
+        assert np.abs(a - b).max() < tol, (tag, name, float(np.abs(a - b).max()))
+
+
+@pytest.mark.parametrize("uint8,bcast", [(False, False), (True, True), (True, False), (False, True)])
+def test_kernel_source_geometry_on_host(emu, fx, uint8, bcast):
+    orig, target = (30, 44), (20, 28)
+    img1, img2, flow, mask, P, _, _ = geometry_case(5 + uint8 + 2 * bcast, 3, orig, target, uint8, bcast)
+    want = oracle_geometry(img1, img2, flow, mask, P, target)
+    assert (want[1][0] == 0).mean() > 0.1 and (want[1][1] == 0).mean() < 0.05      # the zero-padded region is exercised
+    check_geometry(emu_geometry(emu, img1, img2, flow, mask, P, target), want)
+
+
+def test_kernel_source_geometry_on_host_reference_fixture(emu, fx):
+    orig, target = shapes(fx)
+    P = augment_ref.geometry_params(geo_draws(fx), orig, target)
+    got = emu_geometry(emu, fx["img1"], fx["img2"], fx["flow"], fx["mask"], P, target)
+    check_geometry(got, [fx["geo_" + k] for k in ("img1", "img2", "flow", "mask")], "fixture")
+
+
+def test_kernel_source_color_on_host(emu, fx):
+    d = col_draws(fx, "col")
+    P = np.ascontiguousarray(augment_ref.color_params(d, gamma=True))
+    sigma = float(d["noise_sigma"][0])
+    i1, i2 = np.ascontiguousarray(fx["geo_img1"]), np.ascontiguousarray(fx["geo_img2"])
+    n1, n2 = np.ascontiguousarray(d["noise1"]), np.ascontiguousarray(d["noise2"])
+    N, _, H, W = i1.shape
+    # partial sums as color_sum_kernel lays them out: ws[image][n][slice][3]; everything in slice 0 here
+    ws = np.zeros((2, N, 64, 3), np.float32)
+    for k, (img, nz) in enumerate(((i1, n1), (i2, n2))):
+        pre = np.zeros_like(img)
+        emu.emu_color_pre_mean(_ptr(img), _ptr(nz), _ptr(P), ctypes.c_float(sigma), ctypes.c_longlong(0), k, _ptr(pre), N, H, W)
+        ws[k, :, 0, :] = pre.sum(axis=(2, 3), dtype=np.float64)
+    o1, o2 = np.zeros_like(i1), np.zeros_like(i2)
+    emu.emu_color_apply(_ptr(i1), _ptr(i2), _ptr(P), _ptr(n1), _ptr(n2), ctypes.c_float(sigma), ctypes.c_longlong(0), _ptr(ws),
+                        _ptr(o1), _ptr(o2), N, H, W, 1)
+    assert np.abs(o1 - fx["col_img1"]).max() < 2e-5 and np.abs(o2 - fx["col_img2"]).max() < 2e-5
+
+
+def test_kernel_source_philox_noise_on_host(emu):
+    N, H, W, seed = 2, 5, 7, 0x1234567890ABCDEF & 0x7FFFFFFFFFFFFFFF
+    P = np.zeros((N, 26), np.float32)            # zero hue matrix: the pre-mean image IS noise * sigma
+    img = np.zeros((N, 3, H, W), np.float32)
+    for image in (0, 1):
+        pre = np.zeros_like(img)
+        emu.emu_color_pre_mean(_ptr(img), None, _ptr(P), ctypes.c_float(1.0), ctypes.c_longlong(seed), image, _ptr(pre), N, H, W)
+        want = augment_ref.philox_normal(N, H, W, seed, image)
+        assert np.abs(pre - want).max() < 2e-5
+    z = augment_ref.philox_normal(8, 64, 64, 99, 0)
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02     # a standard normal stream
+    # Philox4x32-10 known-answer test (Random123 kat_vectors: counter = key = 0)
+    r = augment_ref.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(x[0]) for x in r] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU: the C ABI against the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("uint8,bcast,N,orig,target", [
+    (False, False, 3, (30, 44), (20, 28)),
+    (True, True, 2, (64, 96), (48, 80)),
+    (True, False, 4, (96, 128), (64, 112)),
+    (False, True, 2, (384, 512), (320, 448)),          # FlyingChairs shapes of main.py (orig 384x512 -> target 320x448)
+])
+def test_geometry_augment_parity(uint8, bcast, N, orig, target):
+    from maskflownet_b200 import augment
+    img1, img2, flow, mask, P, _, _ = geometry_case(17 + N, N, orig, target, uint8, bcast)
+    got = augment.geometry_augment(_cuda(img1), _cuda(img2), _cuda(flow), _cuda(mask), _cuda(P), target)
+    check_geometry([g.cpu().numpy() for g in got], oracle_geometry(img1, img2, flow, mask, P, target), "gpu")
+
+
+@pytest.mark.gpu
+def test_geometry_augment_reference_fixture_and_class(fx):
+    from maskflownet_b200 import augment
+    orig, target = shapes(fx)
+    geo = make_geo(orig, target, 3)
+    d = {k: torch.from_numpy(v) for k, v in geo_draws(fx).items()}
+    got = geo(_cuda(fx["img1"]), _cuda(fx["img2"]), _cuda(fx["flow"]), _cuda(fx["mask"]), draws=d)
+    check_geometry([g.cpu().numpy() for g in got], [fx["geo_" + k] for k in ("img1", "img2", "flow", "mask")], "fixture")
+    # own draws: runs, finite, images stay in [0, 1], mask in [0, 1]
+    o1, o2, of, om = geo(_cuda(fx["img1"]), _cuda(fx["img2"]), _cuda(fx["flow"]), _cuda(fx["mask"]))
+    assert all(torch.isfinite(t).all() for t in (o1, o2, of, om))
+    assert 0 <= float(o1.min()) and float(o1.max()) <= 1 and 0 <= float(om.min()) and float(om.max()) <= 1 + 1e-6
+    with pytest.raises(augment.MaskflowError):
+        augment.geometry_augment(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, 8, 8), torch.zeros(1, 2, 8, 8), torch.zeros(1, 1, 8, 8),
+                                 torch.zeros(1, 22), (4, 4))       # CPU tensors: no fallback
+
+
+@pytest.mark.gpu
+def test_color_augment_parity(fx):
+    from maskflownet_b200 import augment
+    d = col_draws(fx, "col")
+    P = augment_ref.color_params(d, gamma=True)
+    sigma = float(d["noise_sigma"][0])
+    o1, o2 = augment.color_augment(_cuda(fx["geo_img1"]), _cuda(fx["geo_img2"]), _cuda(P), noise_sigma=sigma,
+                                   noise=(_cuda(d["noise1"]), _cuda(d["noise2"])), has_gamma=True)
+    assert np.abs(o1.cpu().numpy() - fx["col_img1"]).max() < 2e-5 and np.abs(o2.cpu().numpy() - fx["col_img2"]).max() < 2e-5
+    e = col_draws(fx, "eig")
+    Pe = augment_ref.color_params(e, eigen=True)
+    o1, o2 = augment.color_augment(_cuda(fx["geo_img1"]), _cuda(fx["geo_img2"]), _cuda(Pe))
+    assert np.abs(o1.cpu().numpy() - fx["eig_img1"]).max() < 2e-5 and np.abs(o2.cpu().numpy() - fx["eig_img2"]).max() < 2e-5
+
+
+@pytest.mark.gpu
+def test_color_augment_in_kernel_noise_and_class():
+    from maskflownet_b200 import augment
+    rng = np.random.default_rng(3)
+    N, H, W, seed, sigma = 4, 96, 160, 123456789012345, 0.03
+    i1, i2 = rng.random((N, 3, H, W), dtype=np.float32), rng.random((N, 3, H, W), dtype=np.float32)
+    col = augment.ColorAugmentation(contrast_range=(-0.2, 0.4), brightness_sigma=0.05, channel_range=(0.9, 1.2), batch_size=N,
+                                    shape=(H, W), noise_range=(0, 0.02), saturation=0.25, hue=0.1, gamma_range=(-0.5, 0.5), seed=5)
+    d = col.sample()
+    P = col.params(d)
+    o1, o2 = augment.color_augment(_cuda(i1), _cuda(i2), P.cuda(), noise_sigma=sigma, seed=seed, has_gamma=True)
+    for image, (img, out) in enumerate(((i1, o1), (i2, o2))):
+        want = augment_ref.color_augment_one(img, P.numpy(), noise=augment_ref.philox_normal(N, H, W, seed, image), noise_sigma=sigma)
+        assert np.abs(out.cpu().numpy() - want).max() < 2e-5
+    # bit-reproducible (no atomics), and the class call runs end to end
+    p1, p2 = augment.color_augment(_cuda(i1), _cuda(i2), P.cuda(), noise_sigma=sigma, seed=seed, has_gamma=True)
+    assert torch.equal(p1, o1) and torch.equal(p2, o2)
+    c1, c2 = col(_cuda(i1), _cuda(i2))
+    assert torch.isfinite(c1).all() and 0 <= float(c1.min()) and float(c2.max()) <= 1
