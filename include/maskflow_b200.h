@@ -307,6 +307,24 @@ MFN_API int mfn_color_augment_forward(const float* img1, const float* img2, cons
                                       void* workspace, long long workspace_bytes, int N, int H, int W, int has_gamma,
                                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * MultiscaleEpe('upsampling'), fused: network/MaskFlownet.py:563-611, built in
+ * network/pipeline.py:39-45 (scales 64,32,16,8,4; weights .005,.01,.02,.08,.32), applied in pipeline.py:81-83,107.
+ *   loss[n] = sum_s weights[s] * sum_hw( e_s * mask ) / sum_hw( mask ),
+ *   e_s = sqrt( sum_c (Upsample(scales[s])(preds[s])_c - flow_c)^2 + eps )   or, q >= 0:  ( sum_c |.| + eps )^q   (q < 0: L2)
+ * flow (N,2,H,W) label, mask (N,1,H,W), preds[s] (N,2,H/scales[s],W/scales[s]): device pointers; preds / grad_preds / scales /
+ * weights are HOST arrays of num_scales (<= 8) entries.  forward: loss (N), mask_sum (N) (kept for backward), workspace of
+ * mfn_multiscale_epe_workspace_bytes(N) bytes; one pass over flow and mask, no up-sampled tensor is materialised.
+ * backward: grad_preds[s] (N,2,H/s,W/s) = d( sum_n grad_loss[n] * loss[n] ) / d preds[s], one launch, gather form, no atomics.
+ * ------------------------------------------------------------------------------------------------- */
+MFN_API long long mfn_multiscale_epe_workspace_bytes(int N);
+MFN_API int mfn_multiscale_epe_forward(const float* flow, const float* mask, const float* const* preds, const int* scales,
+                                       const float* weights, int num_scales, float eps, float q, float* loss, float* mask_sum,
+                                       void* workspace, long long workspace_bytes, int N, int H, int W, void* stream);
+MFN_API int mfn_multiscale_epe_backward(const float* flow, const float* mask, const float* const* preds, const int* scales,
+                                        const float* weights, int num_scales, float eps, float q, const float* grad_loss,
+                                        const float* mask_sum, float* const* grad_preds, int N, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

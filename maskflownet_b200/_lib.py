@@ -37,6 +37,8 @@ SIGNATURES = {
     "mfn_postprocess_forward": [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _f],
     "mfn_geometry_augment_forward": [_f, _f, _i, _f, _f, _i, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f],
     "mfn_color_augment_forward": [_f, _f, _f, _f, _f, _fl, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _f],
+    "mfn_multiscale_epe_forward": [_f, _f, _f, _f, _f, _i, _fl, _fl, _f, _f, _f, _ll, _i, _i, _i, _f],
+    "mfn_multiscale_epe_backward": [_f, _f, _f, _f, _f, _i, _fl, _fl, _f, _f, _f, _i, _i, _i, _f],
     "mfn_set_tuning": [ctypes.c_char_p, _i],
     "mfn_conv3x3_pack_weights": [_f, _f, _i, _i, _f],
     "mfn_conv3x3_forward": [_f, _ll, _f, _f, _f, _ll, _i, _i, _i, _i, _i, _i, _fl, _f],
@@ -76,6 +78,8 @@ def lib() -> ctypes.CDLL:
         L.mfn_conv3x3_workspace_bytes.argtypes = [ctypes.c_int] * 7
         L.mfn_color_augment_workspace_bytes.restype = ctypes.c_longlong
         L.mfn_color_augment_workspace_bytes.argtypes = [ctypes.c_int]
+        L.mfn_multiscale_epe_workspace_bytes.restype = ctypes.c_longlong
+        L.mfn_multiscale_epe_workspace_bytes.argtypes = [ctypes.c_int]
         L.mfn_warp_resample_workspace_bytes.restype = ctypes.c_longlong
         L.mfn_warp_resample_workspace_bytes.argtypes = [ctypes.c_int] * 4
         for name, argtypes in SIGNATURES.items():

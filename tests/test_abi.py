@@ -47,7 +47,8 @@ def test_ctypes_table_matches_header():
                 assert ct is ctypes.c_int, (name, a)
     ops_in_header = {n for n in decl if n not in ("mfn_version", "mfn_last_error", "mfn_last_kernel", "mfn_launch_count",
                                                "mfn_conv3x3_packed_bytes", "mfn_warp_resample_workspace_bytes",
-                                               "mfn_conv3x3_workspace_bytes", "mfn_color_augment_workspace_bytes")}
+                                               "mfn_conv3x3_workspace_bytes", "mfn_color_augment_workspace_bytes",
+                                               "mfn_multiscale_epe_workspace_bytes")}
     assert ops_in_header == set(_lib.SIGNATURES), ops_in_header ^ set(_lib.SIGNATURES)
 
 

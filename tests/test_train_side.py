@@ -1,9 +1,11 @@
-"""Row N4: GPU-side training augmentation, /root/reference/augmentation.py:168-339.
+"""The training-side rows of SURVEY.md 8f: N4, GPU-side augmentation (/root/reference/augmentation.py:168-339), and the fused
+MultiscaleEpe of row N2 (network/MaskFlownet.py:563-611).
 
 CPU part (`-m "not gpu"`): the numpy restatement (oracle/augment_ref.py) against the fixture produced by the reference's own
 augmentation.py (tests/golden/make_golden_aug.py); the product's host logic (draws -> parameter blocks) against the oracle;
 and the kernel SOURCE of csrc/augment.cu compiled for the host (tests/host_emu/) against the oracle.
-GPU part (`-m gpu`): mfn_geometry_augment_forward / mfn_color_augment_forward through the C ABI against the oracle.
+GPU part (`-m gpu`): mfn_geometry_augment_forward / mfn_color_augment_forward / mfn_multiscale_epe_* through the C ABI
+against the oracle.
 """
 import ctypes
 import os
@@ -122,13 +124,22 @@ def test_host_sampling_ranges_and_determinism():
 # ---------------------------------------------------------------------------------------------------------------
 # the kernel source compiled for the host (no GPU in the development container)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("emu") / "libaugment_emu.so")
-    src = os.path.join(HERE, "host_emu", "augment_emu.cpp")
+def _build_emu(tmp_path_factory, name):
+    out = str(tmp_path_factory.mktemp("emu") / f"lib{name}.so")
+    src = os.path.join(HERE, "host_emu", name + ".cpp")
     subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(HERE, "host_emu"), "-o", out, src],
                    check=True)
     return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    return _build_emu(tmp_path_factory, "augment_emu")
+
+
+@pytest.fixture(scope="module")
+def emu_loss(tmp_path_factory):
+    return _build_emu(tmp_path_factory, "loss_emu")
 
 
 def _ptr(a):
@@ -300,3 +311,68 @@ def test_color_augment_in_kernel_noise_and_class():
     assert torch.equal(p1, o1) and torch.equal(p2, o2)
     c1, c2 = col(_cuda(i1), _cuda(i2))
     assert torch.isfinite(c1).all() and 0 <= float(c1.min()) and float(c2.max()) <= 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused MultiscaleEpe (row N2): kernel source on the host, then the C ABI on the GPU, against torch autograd of the
+# operator-by-operator composition on the oracle's Upsample
+# ---------------------------------------------------------------------------------------------------------------
+def epe_case(seed, N, H, W, scales):
+    rng = np.random.default_rng(seed)
+    preds = [np.ascontiguousarray(rng.standard_normal((N, 2, H // s, W // s)).astype(np.float32) * 2) for s in scales]
+    flow = (rng.standard_normal((N, 2, H, W)) * 2).astype(np.float32)
+    mask = (rng.random((N, 1, H, W)) > 0.3).astype(np.float32)
+    gl = rng.random(N).astype(np.float32) + 0.5
+    return preds, flow, mask, gl
+
+
+def epe_oracle(preds, flow, mask, gl, scales, weights, eps, q):
+    from maskflownet_b200 import losses
+    from oracle import torch_ref
+    rp = [torch.from_numpy(p).clone().requires_grad_() for p in preds]
+    loss = losses.multiscale_epe(torch.from_numpy(flow), torch.from_numpy(mask), rp, scales=scales, weights=weights, eps=eps, q=q,
+                                 upsample=torch_ref.upsample)
+    (loss * torch.from_numpy(gl)).sum().backward()
+    return loss.detach().numpy(), [p.grad.numpy() for p in rp]
+
+
+@pytest.mark.parametrize("q", [None, 0.4])
+def test_kernel_source_multiscale_epe_on_host(emu_loss, q):
+    scales, weights, eps = (16, 8, 4, 2), (.01, .02, .08, .32), 1e-8 if q is None else 0.01
+    N, H, W = 2, 32, 48
+    preds, flow, mask, gl = epe_case(4, N, H, W, scales)
+    want_loss, want_grads = epe_oracle(preds, flow, mask, gl, scales, weights, eps, q)
+    n = len(scales)
+    pa = (ctypes.c_void_p * n)(*[p.ctypes.data for p in preds])
+    sa, wa = (ctypes.c_int * n)(*scales), (ctypes.c_float * n)(*weights)
+    loss, msum = np.zeros(N, np.float32), np.zeros(N, np.float32)
+    qf = ctypes.c_float(-1.0 if q is None else q)
+    emu_loss.emu_epe_forward(_ptr(flow), _ptr(mask), pa, sa, wa, n, ctypes.c_float(eps), qf, _ptr(loss), _ptr(msum), N, H, W)
+    assert np.abs(loss - want_loss).max() < 1e-5 * max(1.0, np.abs(want_loss).max())
+    assert np.abs(msum - mask.sum(axis=(1, 2, 3))).max() < 0.5
+    grads = [np.full_like(p, np.nan) for p in preds]
+    ga = (ctypes.c_void_p * n)(*[g.ctypes.data for g in grads])
+    emu_loss.emu_epe_backward(_ptr(flow), _ptr(mask), pa, sa, wa, n, ctypes.c_float(eps), qf, _ptr(gl), _ptr(msum), ga, N, H, W)
+    for g, w in zip(grads, want_grads):
+        assert np.isfinite(g).all() and np.abs(g - w).max() < 1e-5 * max(1e-3, np.abs(w).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("q,N,H,W", [(None, 2, 64, 128), (0.4, 3, 128, 192), (None, 8, 384, 512)])
+def test_multiscale_epe_fused_parity(q, N, H, W):
+    from maskflownet_b200 import losses
+    eps = 1e-8 if q is None else 0.01
+    preds, flow, mask, gl = epe_case(9, N, H, W, losses.SCALES)
+    want_loss, want_grads = epe_oracle(preds, flow, mask, gl, losses.SCALES, losses.WEIGHTS, eps, q)
+    gp = [_cuda(p).requires_grad_() for p in preds]
+    loss = losses.multiscale_epe(_cuda(flow), _cuda(mask), gp, eps=eps, q=q)
+    assert loss.shape == (N,) and np.abs(loss.detach().cpu().numpy() - want_loss).max() < 2e-5 * max(1.0, np.abs(want_loss).max())
+    (loss * _cuda(gl)).sum().backward()
+    for a, w in zip(gp, want_grads):
+        assert np.abs(a.grad.cpu().numpy() - w).max() < 2e-5 * max(1e-3, np.abs(w).max())
+    # the unfused composition (ops.upsample + torch) agrees, and the fused path is bit-reproducible
+    gq = [_cuda(p).requires_grad_() for p in preds]
+    ref = losses.multiscale_epe(_cuda(flow), _cuda(mask), gq, eps=eps, q=q, fused=False)
+    assert (ref - loss).abs().max().item() < 2e-5 * max(1.0, float(ref.abs().max()))
+    again = losses.multiscale_epe(_cuda(flow), _cuda(mask), [_cuda(p) for p in preds], eps=eps, q=q)
+    assert torch.equal(again, loss.detach())

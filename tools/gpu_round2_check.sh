@@ -1,12 +1,10 @@
 #!/bin/bash
-# round-2 GPU batch (edited per batch)
+# round-2 GPU batch (edited per batch): the training-side rows (N4 augmentation, fused MultiscaleEpe) + the last warp_lin change
 mkdir -p gpurun_out
-echo "== warp tests"; timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_network_gpu.py -q -m gpu -x -k "warp or linear or network or cascade" 2>&1 | tail -3
-for t in "warp_lin_fch=16" ""; do echo "== kbench warp [$t]"; MFN_TUNING=$t timeout 300 python tools/kbench.py --what warp --levels 2,3,4,5 --iters 20 2>&1 | grep warp_mask | python -c "
+echo "== new + touched tests"; timeout 420 python -m pytest tests/test_train_side.py tests/test_network_gpu.py tests/test_ops_gpu.py -q -m gpu -k "augment or epe or warp or linear or abi" 2>&1 | tail -15 | tee gpurun_out/check_tests.log
+echo "== train-side bench"; timeout 120 python tools/train_side_bench.py > gpurun_out/train_side_bench.jsonl 2> gpurun_out/train_side_bench.err; cat gpurun_out/train_side_bench.jsonl; tail -3 gpurun_out/train_side_bench.err
+echo "== bench fwdbwd"; timeout 240 python bench.py --config fwdbwd --steps 5 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 > gpurun_out/bench_fwdbwd.json; cut -c1-400 gpurun_out/bench_fwdbwd.json
+echo "== bench"; timeout 300 python bench.py --steps 10 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 > gpurun_out/bench_ours_short.json; python -c "
 import sys, json
-for l in sys.stdin:
-    d = json.loads(l); print(d['level'], d['launched'], d['ms_avg'])"; done
-echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read())
+d = json.loads(open('gpurun_out/bench_ours_short.json').read())
 print({k: d[k] for k in ('value', 'ms_per_step', 'ms_per_step_eager')}, d['e2e']['value'], {k: v['ms'] for k, v in d['roofline']['k3_warp_levels'].items()})"
