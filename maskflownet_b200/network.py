@@ -86,6 +86,7 @@ class _FlowNetBase(nn.Module):
     fuse_heads = True   # inference: pred_flow / pred_mask over the block input ride on conv{L}_4's input pass
     use_resample_warp = True   # inference: K3 through linearity (ops.warp_mask(resample=True)) at every level
     use_tc_conv = True   # inference: decoder / context 3x3 convolutions on the fp32-accurate tensor-core kernel (row N2)
+    train_tc_forward = False   # training: 3x3 convolutions run their FORWARD on the same kernel (ops.conv3x3_train), backward cuDNN
 
     def _packed(self, name):
         """Packed split-bf16 weight image of conv `name`, rebuilt when the parameter changes."""
@@ -119,7 +120,8 @@ class _FlowNetBase(nn.Module):
         pm = convs[1] if len(convs) > 1 else None
         if not isinstance(x, _Slab):
             if not self._fast(x):
-                return convs[0](x), (pm(x) if pm is not None else None)
+                return (self._conv_act(f"pred_flow{lvl}", x, 1.0),
+                        self._conv_act(f"pred_mask{lvl}", x, 1.0) if pm is not None else None)
             x = _Slab(x, 0, 0)
         nh = 2 + (1 if pm is not None else 0)
         buf, c0 = x.buf, x.c0
@@ -166,8 +168,17 @@ class _FlowNetBase(nn.Module):
         """3x3 convolution without activation (conv{L}f, dc_conv7)."""
         conv = getattr(self, name)
         if not self._fast(x):
-            return conv(x)
+            return self._conv_act(name, x, 1.0)
         return ops.conv3x3(x, self._packed(name), conv.bias, conv.out_channels, 1.0, conv.dilation[0])
+
+    def _conv_act(self, name, x, slope):
+        """Autograd path of one 3x3 convolution (+ LeakyReLU when slope != 1): torch.nn.functional (cuDNN both ways), or --
+        train_tc_forward -- the tensor-core forward with the cuDNN backward."""
+        conv = getattr(self, name)
+        if self.train_tc_forward and x.is_cuda and conv.kernel_size == (3, 3):
+            return ops.conv3x3_train(x, conv.weight, conv.bias, self._packed(name), slope, conv.dilation[0], conv.stride[0])
+        y = conv(x)
+        return y if slope == 1.0 else tF.leaky_relu(y, slope)
 
     def _fast(self, x):
         return self.use_tc_conv and x.is_cuda and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
@@ -184,7 +195,7 @@ class _FlowNetBase(nn.Module):
                 if fast:
                     x = ops.conv3x3(x, self._packed(name), conv.bias, conv.out_channels, SLOPE, 1, 2 if j == 0 else 1)
                 else:
-                    x = tF.leaky_relu(conv(x), SLOPE)
+                    x = self._conv_act(name, x, SLOPE)
             feats.append(x)
         return feats  # [c?1 .. c?6]
 
@@ -206,7 +217,7 @@ class _FlowNetBase(nn.Module):
             buf[:, tot:].copy_(x)
             return self._dense_inplace(lvl, buf, tot)
         for i in range(5):
-            x = torch.cat([tF.leaky_relu(getattr(self, f"conv{lvl}_{i}")(x), SLOPE), x], dim=1)
+            x = torch.cat([self._conv_act(f"conv{lvl}_{i}", x, SLOPE), x], dim=1)
         return x
 
     def _heads_front(self, lvl) -> int:
@@ -252,7 +263,7 @@ class _FlowNetBase(nn.Module):
             elif fast:
                 x = ops.conv3x3(x, self._packed(f"dc_conv{i}"), conv.bias, conv.out_channels, SLOPE, conv.dilation[0])
             else:
-                x = tF.leaky_relu(conv(x), SLOPE)
+                x = self._conv_act(f"dc_conv{i}", x, SLOPE)
         return self._plain("dc_conv7", x)
 
     def _make_decoder(self, in_ch: Dict[int, int], with_mask: bool, upfeat_ch):

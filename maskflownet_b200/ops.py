@@ -467,6 +467,42 @@ def conv3x3(x: torch.Tensor, packed: torch.Tensor, bias: Optional[torch.Tensor],
     return out
 
 
+class _Conv3x3TrainFn(torch.autograd.Function):
+    """Training-mode 3x3 convolution (+ bias + LeakyReLU): FORWARD on the tcgen05 kernel (the same launch inference uses),
+    BACKWARD through aten.convolution_backward (cuDNN dgrad / wgrad -- this library has no convolution backward kernels,
+    DESIGN.md section 7).  The activation's backward uses the saved OUTPUT (y > 0  <=>  pre-activation > 0 for slope > 0)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, packed, slope, dilation, stride):
+        y = conv3x3(x, packed, bias, weight.shape[0], slope, dilation, stride)      # grad mode is off inside forward()
+        ctx.save_for_backward(x, weight, y)
+        ctx.cfg = (float(slope), int(dilation), int(stride), bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, y = ctx.saved_tensors
+        slope, dilation, stride, has_bias = ctx.cfg
+        if slope != 1.0:
+            g = torch.where(y > 0, g, g * slope)
+        gx, gw, gb = torch.ops.aten.convolution_backward(
+            g.contiguous(), x, weight, [weight.shape[0]] if has_bias else None, [stride, stride], [dilation, dilation],
+            [dilation, dilation], False, [0, 0], 1,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]])
+        return gx, gw, (gb if has_bias else None), None, None, None, None
+
+
+def conv3x3_train(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], packed: torch.Tensor,
+                  leaky_slope: float = 0.1, dilation: int = 1, stride: int = 1) -> torch.Tensor:
+    """LeakyReLU(conv3x3(x, weight) + bias) with autograd: tensor-core forward, cuDNN backward (see _Conv3x3TrainFn).
+    `packed` = conv3x3_pack(weight) for the CURRENT value of weight (network._packed re-packs when the parameter's version
+    changes, i.e. after every optimizer step)."""
+    x = _chk(x, "conv3x3_train.x")
+    if weight.dim() != 4 or tuple(weight.shape[2:]) != (3, 3) or weight.shape[1] != x.shape[1]:
+        raise MaskflowError(f"conv3x3_train: weight {tuple(weight.shape)} does not fit x {tuple(x.shape)}")
+    return _Conv3x3TrainFn.apply(x, weight, bias, packed, leaky_slope, dilation, stride)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # Pre / post-processing around the network (row N3)
 # ----------------------------------------------------------------------------------------------------------
