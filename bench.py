@@ -428,6 +428,8 @@ def bench_other(args, K, Wm):
         workload = ("MaskFlownet-S training step (fwd + bwd + one NCCL gradient all-reduce + Adam), batch 4 per GPU "
                     f"(global {4 * c.world}), 960x540 padded to 960x576 as do_batch_mx does -- BASELINE configs[4]")
         model = network.MaskFlownetS().to(c.dev).train()
+    if args.train_tc_forward >= 0:
+        model.train_tc_forward = bool(args.train_tc_forward)
     a_h, b_h = synthetic_pairs(BATCH, 100 + c.rank, H, W)
     a_h, b_h = a_h.pin_memory(), b_h.pin_memory()
     a_d, b_d = a_h.to(c.dev), b_h.to(c.dev)
@@ -527,6 +529,9 @@ def main():
     ap.add_argument("--config", default="fwd", choices=["fwd", "fwdbwd", "cascade", "train8"])
     ap.add_argument("--cpu-sample-steps", type=int, default=32)   # ~10 s of host work on a 16-thread box
     ap.add_argument("--sustain-seconds", type=float, default=3.0)
+    ap.add_argument("--train-tc-forward", type=int, default=-1,
+                    help="fwdbwd / train8: 1 = the 3x3 convolutions' forward on the tcgen05 kernel (cuDNN backward), 0 = cuDNN "
+                         "both ways, -1 = the model's default")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

@@ -74,12 +74,16 @@ __device__ __forceinline__ Taps sampler_taps(float gx, float gy, int H, int W) {
   return t;
 }
 
+// uint8 sources are read as value / 255 (network/pipeline.py:100).  The 28 taps of a pixel would cost 28 IEEE divisions
+// (~10 instructions each; the first version of the kernel spent most of its issue slots there: 0.18 ms for 8 x 448 x 832
+// target pixels, profiles/r02_train_side_bench.jsonl): the 256 possible quotients are tabulated once per block instead --
+// the same correctly rounded values, one shared-memory load per tap.
 template <typename T>
-__device__ __forceinline__ float ld(const T* p, int o, float div) {
-  return __fdiv_rn((float)p[o], div);
+__device__ __forceinline__ float ld(const T* p, int o, const float* lut) {
+  return lut[__ldg(p + o)];
 }
 template <>
-__device__ __forceinline__ float ld<float>(const float* p, int o, float) {
+__device__ __forceinline__ float ld<float>(const float* p, int o, const float*) {
   return __ldg(p + o);
 }
 
@@ -89,12 +93,17 @@ __global__ void __launch_bounds__(256)
     geometry_augment_kernel(const T* __restrict__ img1, const T* __restrict__ img2, const float* __restrict__ flow,
                             const T* __restrict__ mask, int mask_broadcast, const float* __restrict__ params,
                             float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ of, float* __restrict__ om, int N,
-                            int H, int W, int TH, int TW, float sx, float sy, float div) {
+                            int H, int W, int TH, int TW, float sx, float sy, float divisor) {
   const int tplane = TH * TW;
   const size_t plane = (size_t)H * W;
   const long long total = (long long)N * tplane;
   const float x1 = __fadd_rn(-1.f, __fmul_rn((float)(TW - 1), sx)), y1 = __fadd_rn(-1.f, __fmul_rn((float)(TH - 1), sy));
   const float half_w = (float)(0.5 * (double)(W - 1)), half_h = (float)(0.5 * (double)(H - 1));
+  __shared__ float div[256];
+  if (sizeof(T) == 1) {
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) div[v] = __fdiv_rn((float)v, divisor);
+    __syncthreads();
+  }
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(idx / tplane), rem = (int)(idx - (long long)n * tplane);
     const int ty = rem / TW, tx = rem - ty * TW;

@@ -24,7 +24,9 @@ extern "C" __attribute__((visibility("default"))) void emu_geometry_augment(
     const void* img1, const void* img2, int is_uint8, const float* flow, const void* mask, int mask_broadcast,
     const float* params, float* o1, float* o2, float* of, float* om, int N, int H, int W, int TH, int TW) {
   const float sx = (float)(2.0 / (double)(TW - 1)), sy = (float)(2.0 / (double)(TH - 1));   // as mfn_geometry_augment_forward
-  for_each_thread(dim3(3), dim3(64), [&] {
+  // two passes: the kernel's per-block table of v / 255 is filled by ALL threads of a block before the barrier; the shim's
+  // __shared__ is static and its threads run one after the other, so the first pass fills the table, the second computes
+  for (int pass = 0; pass < 2; ++pass) for_each_thread(dim3(3), dim3(64), [&] {
     if (is_uint8)
       geometry_augment_kernel<unsigned char>((const unsigned char*)img1, (const unsigned char*)img2, flow,
                                              (const unsigned char*)mask, mask_broadcast, params, o1, o2, of, om, N, H, W, TH, TW,

@@ -376,3 +376,82 @@ def test_multiscale_epe_fused_parity(q, N, H, W):
     assert (ref - loss).abs().max().item() < 2e-5 * max(1.0, float(ref.abs().max()))
     again = losses.multiscale_epe(_cuda(flow), _cuda(mask), [_cuda(p) for p in preds], eps=eps, q=q)
     assert torch.equal(again, loss.detach())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training-mode convolutions: tensor-core forward + cuDNN backward (ops.conv3x3_train, network.train_tc_forward)
+# ---------------------------------------------------------------------------------------------------------------
+def test_conv3x3_train_backward_wiring_on_cpu(monkeypatch):
+    """The autograd wiring of ops._Conv3x3TrainFn (activation mask from the saved output, aten.convolution_backward argument
+    order, frozen input, missing bias) against plain autograd, with the CUDA forward replaced by a torch stub."""
+    import torch.nn.functional as tF
+    from maskflownet_b200 import ops
+
+    def stub(x, packed, bias, Cout, slope, dil, stride):
+        y = tF.conv2d(x, packed, bias, stride=stride, padding=dil, dilation=dil)
+        return y if slope == 1.0 else tF.leaky_relu(y, slope)
+    monkeypatch.setattr(ops, "conv3x3", stub)
+    torch.manual_seed(0)
+    for slope, dil, stride, has_bias in [(0.1, 1, 1, True), (0.1, 1, 2, True), (1.0, 1, 1, True), (0.1, 4, 1, True), (0.1, 1, 1, False)]:
+        x = torch.randn(2, 5, 9, 11, requires_grad=True)
+        w = torch.randn(4, 5, 3, 3, requires_grad=True)
+        b = torch.randn(4, requires_grad=True) if has_bias else None
+        y = ops._Conv3x3TrainFn.apply(x, w, b, w.detach(), slope, dil, stride)
+        g = torch.randn_like(y)
+        y.backward(g)
+        got = [t.grad.clone() for t in (x, w) + ((b,) if has_bias else ())]
+        for t in (x, w) + ((b,) if has_bias else ()):
+            t.grad = None
+        stub(x, w, b, 4, slope, dil, stride).backward(g)
+        for a, t in zip(got, (x, w) + ((b,) if has_bias else ())):
+            assert torch.allclose(a, t.grad, atol=1e-6)
+    x = torch.randn(2, 3, 8, 8)                                     # the image layer: no input gradient requested
+    w = torch.randn(4, 3, 3, 3, requires_grad=True)
+    ops._Conv3x3TrainFn.apply(x, w, None, w.detach(), 0.1, 1, 2).sum().backward()
+    assert w.grad.abs().sum() > 0
+
+
+@pytest.mark.gpu
+def test_conv3x3_train_matches_cudnn_autograd():
+    import torch.nn.functional as tF
+    from maskflownet_b200 import ops
+    torch.manual_seed(1)
+    for Cin, Cout, H, W, dil, stride in [(16, 32, 24, 40, 1, 1), (3, 16, 32, 64, 1, 2), (128, 96, 16, 32, 8, 1)]:
+        x = torch.randn(2, Cin, H, W, device="cuda", requires_grad=Cin != 3)
+        w = (torch.randn(Cout, Cin, 3, 3, device="cuda") * (2.0 / (9 * Cin)) ** 0.5).requires_grad_()
+        b = (torch.randn(Cout, device="cuda") * 0.1).requires_grad_()
+        y = ops.conv3x3_train(x, w, b, ops.conv3x3_pack(w), 0.1, dil, stride)
+        ref = tF.leaky_relu(tF.conv2d(x, w, b, stride=stride, padding=dil, dilation=dil), 0.1)
+        assert (y - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+        g = torch.randn_like(ref)
+        gy = torch.autograd.grad(y, [w, b] + ([x] if x.requires_grad else []), g)
+        gr = torch.autograd.grad(ref, [w, b] + ([x] if x.requires_grad else []), g)
+        for a, r in zip(gy, gr):      # the activation masks agree except where |pre-activation| < the forward's 1e-5 error
+            assert (a - r).abs().max().item() < 2e-3 * max(1.0, r.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_training_step_with_tensor_core_forward_matches_cudnn_forward():
+    """One MaskFlownet-S training step (MultiscaleEpe loss) with train_tc_forward on / off: same loss, same gradients up to the
+    1e-5-relative difference of the two forward convolutions."""
+    from maskflownet_b200 import losses, network
+    torch.manual_seed(3)
+    model = network.MaskFlownetS().cuda().train()
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand(2, 3, 128, 192, generator=g).cuda() - 0.5
+    b = torch.rand(2, 3, 128, 192, generator=g).cuda() - 0.5
+    flow = (torch.randn(2, 2, 128, 192, generator=g) * 2).cuda()
+    mask = torch.ones(2, 1, 128, 192).cuda()
+    res = {}
+    for mode in (False, True):
+        model.train_tc_forward = mode
+        model.zero_grad(set_to_none=True)
+        preds = model(a, b)[0]
+        loss = losses.multiscale_epe(flow, mask, preds).sum()
+        loss.backward()
+        res[mode] = (loss.item(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    assert abs(res[True][0] - res[False][0]) < 1e-4 * max(1.0, abs(res[False][0]))
+    assert res[True][1].keys() == res[False][1].keys() and len(res[True][1]) > 100
+    worst = max(((res[True][1][k] - res[False][1][k]).abs().max().item() / max(res[False][1][k].abs().max().item(), 1e-6), k)
+                for k in res[False][1])
+    assert worst[0] < 2e-2, worst

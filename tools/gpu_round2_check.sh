@@ -1,10 +1,7 @@
 #!/bin/bash
-# round-2 GPU batch (edited per batch): the training-side rows (N4 augmentation, fused MultiscaleEpe) + the last warp_lin change
+# round-2 GPU batch (edited per batch): hybrid training convolution, geometry kernel with the v/255 table, ncu of the new kernels
 mkdir -p gpurun_out
-echo "== new + touched tests"; timeout 420 python -m pytest tests/test_train_side.py tests/test_network_gpu.py tests/test_ops_gpu.py -q -m gpu -k "augment or epe or warp or linear or abi" 2>&1 | tail -15 | tee gpurun_out/check_tests.log
-echo "== train-side bench"; timeout 120 python tools/train_side_bench.py > gpurun_out/train_side_bench.jsonl 2> gpurun_out/train_side_bench.err; cat gpurun_out/train_side_bench.jsonl; tail -3 gpurun_out/train_side_bench.err
-echo "== bench fwdbwd"; timeout 240 python bench.py --config fwdbwd --steps 5 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 > gpurun_out/bench_fwdbwd.json; cut -c1-400 gpurun_out/bench_fwdbwd.json
-echo "== bench"; timeout 300 python bench.py --steps 10 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 > gpurun_out/bench_ours_short.json; python -c "
-import sys, json
-d = json.loads(open('gpurun_out/bench_ours_short.json').read())
-print({k: d[k] for k in ('value', 'ms_per_step', 'ms_per_step_eager')}, d['e2e']['value'], {k: v['ms'] for k, v in d['roofline']['k3_warp_levels'].items()})"
+echo "== train-side tests"; timeout 300 python -m pytest tests/test_train_side.py -q -m gpu 2>&1 | tail -8 | tee gpurun_out/check_tests2.log
+echo "== train-side bench"; timeout 120 python tools/train_side_bench.py > gpurun_out/train_side_bench2.jsonl 2> gpurun_out/train_side_bench2.err; cut -c1-200 gpurun_out/train_side_bench2.jsonl; tail -3 gpurun_out/train_side_bench2.err
+echo "== bench fwdbwd tc forward"; timeout 240 python bench.py --config fwdbwd --train-tc-forward 1 --steps 5 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 > gpurun_out/bench_fwdbwd_tc.json; cut -c1-330 gpurun_out/bench_fwdbwd_tc.json
+echo "== ncu"; timeout 240 ncu --set full --clock-control none --import-source on -k regex:"geometry_augment|color_|epe_" -c 14 -f -o gpurun_out/prof_train_side python tools/prof_train_side.py > gpurun_out/ncu_train_side.log 2>&1; echo "rc=$?"; ls -la gpurun_out/*.ncu-rep
