@@ -86,7 +86,10 @@ class _FlowNetBase(nn.Module):
     fuse_heads = True   # inference: pred_flow / pred_mask over the block input ride on conv{L}_4's input pass
     use_resample_warp = True   # inference: K3 through linearity (ops.warp_mask(resample=True)) at every level
     use_tc_conv = True   # inference: decoder / context 3x3 convolutions on the fp32-accurate tensor-core kernel (row N2)
-    train_tc_forward = False   # training: 3x3 convolutions run their FORWARD on the same kernel (ops.conv3x3_train), backward cuDNN
+    # training (grad enabled): the 3x3 convolutions still run their FORWARD on the tcgen05 kernel (ops.conv3x3_train: bias +
+    # LeakyReLU fused, the output doubles as the activation mask), the BACKWARD is aten.convolution_backward (cuDNN fp32).
+    # Measured on BASELINE configs[2] (batch 8, 512x384, fwd + bwd): 66.4 -> 52.7 ms per step.  False: cuDNN both ways.
+    train_tc_forward = True
 
     def _packed(self, name):
         """Packed split-bf16 weight image of conv `name`, rebuilt when the parameter changes."""
