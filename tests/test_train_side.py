@@ -432,12 +432,20 @@ def test_conv3x3_train_matches_cudnn_autograd():
         ref = tF.leaky_relu(tF.conv2d(x, w, b, stride=stride, padding=dil, dilation=dil), 0.1)
         err = (y - ref).abs().max().item()
         assert err < 1e-4 * max(1.0, ref.abs().max().item()), (Cin, Cout, dil, stride, err, ref.abs().max().item())
+        # backward: the same activation mask on both sides (ours comes from the saved output; a pre-activation within the
+        # forward's 1e-5 of zero may legitimately fall on the other side of the LeakyReLU kink in the cuDNN forward, which
+        # moves single weight-gradient entries by O(|g x|) -- seen on the B200: 1 of 98 k outputs flipped), so the
+        # reference is the LINEAR convolution's autograd fed with the masked gradient
         g = torch.randn_like(ref)
-        gy = torch.autograd.grad(y, [w, b] + ([x] if x.requires_grad else []), g)
-        gr = torch.autograd.grad(ref, [w, b] + ([x] if x.requires_grad else []), g)
-        for a, r in zip(gy, gr):      # the activation masks agree except where |pre-activation| < the forward's 1e-5 error
-            assert (a - r).abs().max().item() < 2e-3 * max(1.0, r.abs().max().item()), (Cin, Cout, dil, stride, tuple(a.shape),
+        wrt = [w, b] + ([x] if x.requires_grad else [])
+        gy = torch.autograd.grad(y, wrt, g)
+        lin = tF.conv2d(x, w, b, stride=stride, padding=dil, dilation=dil)
+        gr = torch.autograd.grad(lin, wrt, torch.where(y.detach() > 0, g, g * 0.1))
+        for a, r in zip(gy, gr):
+            assert (a - r).abs().max().item() < 1e-4 * max(1.0, r.abs().max().item()), (Cin, Cout, dil, stride, tuple(a.shape),
                                                                                       (a - r).abs().max().item(), r.abs().max().item())
+        flips = ((y.detach() > 0) != (ref.detach() > 0)).float().mean().item()
+        assert flips < 1e-4, flips
 
 
 @pytest.mark.gpu
