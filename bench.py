@@ -490,15 +490,21 @@ def bench_other(args, K, Wm):
     sampler = ClockSampler(c.local)
     sampler.start()
     n0 = _lib.launch_count()
+    torch.cuda.profiler.start()           # ncu --profile-from-start off: the launch list of the timed region only
     ms_total = timed(c, step_resident, K)
+    torch.cuda.profiler.stop()
     launches = _lib.launch_count() - n0
     ar_ms = sum(x.elapsed_time(y) for x, y in t_ar) / len(t_ar) if t_ar else None
     ms_e2e = timed(c, step_e2e, K)
     clocks = sampler.finish()
     pairs = BATCH * K * c.world
+    tc_fwd = bool(getattr(model, "train_tc_forward", False))
     config = {"workload": workload, "arithmetic": ARITH if cfg == "cascade" else
-              "forward/backward of the hot path: our exact-fp32 / bf16-split kernels; dense convolutions in training mode: "
-              "torch autograd (cuDNN fp32, TF32 off)",
+              "forward/backward of the hot path (correlation, fused warp): our exact-fp32 / bf16-split kernels; 3x3 convolutions: "
+              + ("forward on the tcgen05 kernel (f32 I/O, bf16 hi/lo split MMA, fp32 accumulate), backward aten.convolution_backward "
+                 "(cuDNN fp32, TF32 off)" if tc_fwd else "torch autograd both ways (cuDNN fp32, TF32 off)")
+              + "; MultiscaleEpe: fused forward / backward kernels (csrc/loss.cu)",
+              "train_tc_forward": tc_fwd,
               "global_batch": BATCH * c.world,
               "parallelism": (f"data parallel x{c.world}: batch sharded, one NCCL all-reduce of the flat fp32 gradient bucket per step"
                               if cfg == "train8" else f"replicas x{c.world}"),

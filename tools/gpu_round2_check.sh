@@ -1,7 +1,5 @@
 #!/bin/bash
-# round-2 final GPU batch: full GPU suite, configs[2] and configs[1] bench lines, smoke
+# round-2 last GPU batch: launch list of one configs[2] step (who owns the 52 ms), configs[4] step on one GPU
 mkdir -p gpurun_out
-echo "== pytest -m gpu"; timeout 250 python -m pytest tests -q -m gpu --tb=short > gpurun_out/pytest_full.log 2>&1; echo "rc=$?"; tail -14 gpurun_out/pytest_full.log | cut -c1-300
-echo "== bench fwdbwd"; timeout 120 python bench.py --config fwdbwd --steps 10 --warmup 3 --cpu-sample-steps 0 2>&1 | tail -1 > gpurun_out/bench_fwdbwd_final.json; cut -c1-330 gpurun_out/bench_fwdbwd_final.json
-echo "== bench ours"; timeout 200 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_ours.json; cut -c1-300 gpurun_out/bench_ours.json
-echo "== smoke"; timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== launch list fwdbwd"; timeout 100 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_fwdbwd.csv python bench.py --config fwdbwd --steps 1 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 > gpurun_out/launches_fwdbwd.log 2>&1; echo "rc=$?"; wc -l gpurun_out/launches_fwdbwd.csv
+echo "== train step, one rank"; timeout 80 python bench.py --config train8 --steps 5 --warmup 3 --cpu-sample-steps 0 --sustain-seconds 0 2>&1 | tail -1 > gpurun_out/bench_train_1rank.json; cut -c1-250 gpurun_out/bench_train_1rank.json
