@@ -19,7 +19,9 @@ the 1e-4 bound of north_star; no cuDNN / cuBLAS kernel runs in the step).
                    capture of the same kernel (static: ncu cannot run inside the timed region)
   cpu_baseline     oracle port of the whole forward on the host cores + the correlation-only table of BASELINE.md section 3
                    (1-thread literal MXNet loop nest / OpenMP all cores / torch-CPU) per pair, configs[0] first
---config fwdbwd  (configs[2])  MaskFlownet-S forward + MultiscaleEpe + backward, batch 8, 512x384
+--config fwdbwd  (configs[2])  MaskFlownet-S forward + MultiscaleEpe + backward, batch 8, 512x384 (3x3 convolutions: forward
+                               on the tcgen05 kernel, backward cuDNN fp32 -- `--train-tc-forward 0` = cuDNN both ways;
+                               MultiscaleEpe = the fused kernels of csrc/loss.cu)
 --config cascade (configs[3])  MaskFlownet (S head + dual pyramid, md=2 correlations) forward, batch 4, 1024x448
 --config train8  (configs[4])  training step, batch 4 per GPU (32 on 8 GPUs), 960x540 padded to 960x576 like
                                do_batch_mx (network/pipeline.py:122-130): fwd + bwd + ONE NCCL all-reduce + Adam

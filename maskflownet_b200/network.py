@@ -12,8 +12,10 @@ unrolled reference code: one loop over pyramid levels in which
                                                                     -> one launch of ops.image_warp_concat (K5)
 
 The dense 3x3 / transposed convolutions (about 98 % of the FLOPs; row N2) run on the tcgen05 / TMEM
-kernel of csrc/conv3x3_umma.cu at inference (`_fast`): f32 in / out, bf16 hi+lo split operands, fp32 accumulation; with
-gradients enabled they go through torch.nn.functional (autograd).  Sub-module names equal the reference's gluon prefixes (conv1a ... deform5, conv5f,
+kernel of csrc/conv3x3_umma.cu: f32 in / out, bf16 hi+lo split operands, fp32 accumulation.  At inference (`_fast`) with
+in-place concat buffers and fused heads; with gradients enabled (`train_tc_forward`, default) every 3x3 convolution still
+runs its FORWARD on that kernel and its backward through aten.convolution_backward (ops.conv3x3_train), the transposed
+convolutions and the concats through torch autograd.  Sub-module names equal the reference's gluon prefixes (conv1a ... deform5, conv5f,
 dc_conv7 ...) so that shipped .params checkpoints map by name (maskflownet_b200.params).
 
 All flows are (y, x)-ordered and in units of pixels/scale, as in the reference (pipeline.py:105, MaskFlownet.py:69).
