@@ -59,6 +59,7 @@ class _MultiscaleEpeFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         flow, mask, msum, *preds = ctx.saved_tensors
         scales, weights, eps, q = ctx.cfg

@@ -180,7 +180,8 @@ class _FlowNetBase(nn.Module):
         """Autograd path of one 3x3 convolution (+ LeakyReLU when slope != 1): torch.nn.functional (cuDNN both ways), or --
         train_tc_forward -- the tensor-core forward with the cuDNN backward."""
         conv = getattr(self, name)
-        if self.train_tc_forward and x.is_cuda and conv.kernel_size == (3, 3):
+        if (self.train_tc_forward and x.is_cuda and conv.kernel_size == (3, 3) and conv.padding == conv.dilation
+                and conv.stride[0] == conv.stride[1] and conv.groups == 1):
             return ops.conv3x3_train(x, conv.weight, conv.bias, self._packed(name), slope, conv.dilation[0], conv.stride[0])
         y = conv(x)
         return y if slope == 1.0 else tF.leaky_relu(y, slope)

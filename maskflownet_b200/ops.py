@@ -480,6 +480,7 @@ class _Conv3x3TrainFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         x, weight, y = ctx.saved_tensors
         slope, dilation, stride, has_bias = ctx.cfg
