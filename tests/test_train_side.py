@@ -473,3 +473,101 @@ def test_training_step_with_tensor_core_forward_matches_cudnn_forward():
     worst = max(((res[True][1][k] - res[False][1][k]).abs().max().item() / max(res[False][1][k].abs().max().item(), 1e-6), k)
                 for k in res[False][1])
     assert worst[0] < 2e-2, worst
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pipeline.PipelineFlownet (the reference's network/pipeline.py:19-223): host plumbing on the CPU with the CUDA operators
+# replaced by the oracle; the same calls on the GPU
+# ---------------------------------------------------------------------------------------------------------------
+class _TinyNet(torch.nn.Module):
+    """Stand-in for MaskFlownetS with the same output contract: ([flow6..flow2], [mask2], None)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(6, 3, 3, padding=1)
+
+    def forward(self, a, b):
+        import torch.nn.functional as tF
+        y = self.conv(torch.cat([a, b], dim=1))
+        preds = [tF.avg_pool2d(y[:, :2], s) * 20.0 for s in (64, 32, 16, 8, 4)]
+        return preds, [torch.sigmoid(tF.avg_pool2d(y[:, 2:3], 4))], None
+
+
+def _cpu_pipeline(monkeypatch):
+    from maskflownet_b200 import network, ops, pipeline
+    from oracle import cref, prepost_ref, torch_ref
+    t = torch.from_numpy
+    monkeypatch.setattr(network, "MaskFlownetS", _TinyNet)
+    monkeypatch.setattr(ops, "upsample", lambda x, f, scale=1.0: torch_ref.upsample(x, f) * scale)
+    monkeypatch.setattr(ops, "preprocess", lambda a, b, hw=None: tuple(t(v) for v in prepost_ref.preprocess(a.numpy(), b.numpy(), hw)))
+    monkeypatch.setattr(ops, "postprocess", lambda p, H, W, flip_channels=True, is_flow=True: t(
+        prepost_ref.postprocess(p.numpy(), H, W, flip_channels, is_flow)))
+    monkeypatch.setattr(ops, "grid_generator_warp", lambda f: t(cref.grid_generator_warp(f.numpy())))
+    monkeypatch.setattr(ops, "bilinear_sampler", lambda d, g: t(cref.bilinear_sampler(d.numpy(), g.numpy())))
+    return pipeline.PipelineFlownet(device="cpu", lr_schedule=[(2, 1e-4), (5, 5e-5)])
+
+
+def test_pipeline_host_plumbing_on_cpu(monkeypatch):
+    pipe = _cpu_pipeline(monkeypatch)
+    rng = np.random.default_rng(0)
+    n, H, W = 2, 128, 192
+
+    def geo(i1, i2, fl, mk):          # stand-in with the augmentation's contract: uint8 in, float32 [0,1] + (x,y) flow + mask out
+        return i1.float() / 255, i2.float() / 255, fl.clone(), (mk.float() / 255).expand(n, 1, H, W).contiguous()
+    img1 = rng.integers(0, 256, (n, 3, H, W), dtype=np.uint8)
+    img2 = rng.integers(0, 256, (n, 3, H, W), dtype=np.uint8)
+    label = (rng.standard_normal((n, 2, H, W)) * 2).astype(np.float32)
+    w0 = pipe.network.conv.weight.detach().clone()
+    out = pipe.train_batch(img1, img2, label, geo, lambda a, b: (a, b))
+    assert np.isfinite(out["epe"]) and out["epe"] > 0
+    assert not torch.equal(pipe.network.conv.weight, w0)                  # the optimizer stepped
+    g = pipe._bucket.flat.clone()
+    out2 = pipe.train_batch(img1, img2, label, geo, lambda a, b: (a, b), global_batch=4 * n)
+    assert np.isfinite(out2["epe"]) and pipe._bucket.flat.abs().max() < g.abs().max()      # gradients rescaled by 1 / global batch
+    # learning-rate schedule (pipeline.py:65-76)
+    assert pipe.set_learning_rate(1) and pipe.lr == 1e-4 and pipe.set_learning_rate(3) and pipe.lr == 5e-5
+    assert pipe.trainer.param_groups[0]["lr"] == 5e-5 and not pipe.set_learning_rate(9)
+    # validation / prediction loops over lists of HWC samples of a size that needs the x64 resize
+    Hs, Ws = 100, 150
+    s1 = [rng.integers(0, 256, (Hs, Ws, 3), dtype=np.uint8) for _ in range(3)]
+    s2 = [rng.integers(0, 256, (Hs, Ws, 3), dtype=np.uint8) for _ in range(3)]
+    lab = [(rng.standard_normal((Hs, Ws, 2)) * 3).astype(np.float32) for _ in range(3)]
+    epe = pipe.validate(s1, s2, lab, batch_size=2)
+    f1 = pipe.validate(s1, s2, lab, batch_size=2, return_type="f1")
+    assert np.isfinite(epe) and epe > 0 and 0 <= f1 <= 1
+    res = list(pipe.predict(s1, s2, batch_size=2))
+    assert len(res) == 3 and res[0][0].shape == (Hs, Ws, 2) and res[0][1].shape == (Hs, Ws, 1) and res[0][2].shape == (Hs, Ws, 3)
+    # predict's flow is do_batch's flow, channels-last and flipped to (x, y)
+    a = torch.from_numpy(np.transpose(np.stack(s1[:1]), (0, 3, 1, 2)).copy())
+    b = torch.from_numpy(np.transpose(np.stack(s2[:1]), (0, 3, 1, 2)).copy())
+    flow, _, warp, _ = pipe.do_batch(a, b)
+    assert np.allclose(res[0][0], flow[0].permute(1, 2, 0).flip(-1).numpy()) and warp.shape == (1, 3, Hs, Ws)
+    with pytest.raises(Exception):
+        pipe.fix_head()                      # only the cascade has a head to freeze
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first run on hardware happens at round end: the round's GPU allowance was spent before "
+                                        "pipeline.py was written (host plumbing is covered by the CPU test above)")
+def test_pipeline_train_validate_predict_on_gpu():
+    from maskflownet_b200 import augment, pipeline
+    rng = np.random.default_rng(1)
+    n, orig, target = 2, (160, 224), (128, 192)
+    pipe = pipeline.PipelineFlownet(lr_schedule=[(10, 1e-4)])
+    geo = augment.GeometryAugmentation(angle_range=(-17, 17), zoom_range=(0.5, 1 / 0.9), aspect_range=(0.9, 1 / 0.9),
+                                       translation_range=0.1, target_shape=target, orig_shape=orig, batch_size=n,
+                                       relative_angle=0.25, relative_scale=(0.96, 1 / 0.96), relative_translation=0.25, seed=3)
+    col = augment.ColorAugmentation(contrast_range=(-0.4, 0.8), brightness_sigma=0.1, channel_range=(0.8, 1.4), batch_size=n,
+                                    shape=target, noise_range=(0, 0.04), saturation=0.5, hue=0.5, seed=4)
+    img1 = rng.integers(0, 256, (n, 3) + orig, dtype=np.uint8)
+    img2 = rng.integers(0, 256, (n, 3) + orig, dtype=np.uint8)
+    label = (rng.standard_normal((n, 2) + orig) * 2).astype(np.float32)
+    w0 = pipe.network.conv2_0.weight.detach().clone()
+    out = pipe.train_batch(img1, img2, label, geo, col)
+    assert np.isfinite(out["epe"]) and not torch.equal(pipe.network.conv2_0.weight, w0)
+    s1 = [rng.integers(0, 256, (100, 150, 3), dtype=np.uint8) for _ in range(2)]
+    s2 = [rng.integers(0, 256, (100, 150, 3), dtype=np.uint8) for _ in range(2)]
+    lab = [(rng.standard_normal((100, 150, 2)) * 3).astype(np.float32) for _ in range(2)]
+    assert np.isfinite(pipe.validate(s1, s2, lab, batch_size=2))
+    res = list(pipe.predict(s1, s2, batch_size=2))
+    assert len(res) == 2 and res[0][0].shape == (100, 150, 2) and np.isfinite(res[0][0]).all() and res[0][2].shape == (100, 150, 3)
