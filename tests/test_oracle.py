@@ -70,6 +70,19 @@ def test_deformable_conv_fixture_and_identities():
         assert np.abs(t - cref.deformable_conv_forward(x, off, w, b, border_mode=mode)).max() < 2e-5
 
 
+def test_deformable_lower_band_matches_tvm_reference():
+    """MXNet-1.5 border rule, lower half -- a tap whose coordinate lies in (-1, 0) contributes zero -- against TVM's independent
+    pure-python reference (tests/golden/make_golden_deform_tvm.py): 221 taps of the fixture sit in such a band, none in the
+    upper band (where TVM and MXNet 1.5 differ).  The zero-corner rule must NOT match there."""
+    d = np.load(os.path.join(G, "deform_tvm_lowband.npz"))
+    mx15 = cref.deformable_conv_forward(d["x"], d["off"], d["w"], None, border_mode=0)
+    assert np.abs(mx15 - d["out"]).max() < 2e-5
+    zc = cref.deformable_conv_forward(d["x"], d["off"], d["w"], None, border_mode=1)
+    assert np.abs(zc - d["out"]).max() > 1e-2
+    t = torch_ref.deformable_conv(torch.from_numpy(d["x"]), torch.from_numpy(d["off"]), torch.from_numpy(d["w"]), None, 0).numpy()
+    assert np.abs(t - d["out"]).max() < 2e-5                                    # the differentiable restatement too
+
+
 def test_deformable_border_rule_mxnet15():
     """The MXNet-1.5 rule on a 1-channel ramp with a centre-tap delta kernel: zero for coordinate < 0, last pixel (no
     blend) for H-1 < h < H, zero for h >= H."""
