@@ -18,9 +18,11 @@
  *
  * PARITY PIN STATUS: the reference ships no tests / golden vectors and MXNet cannot be installed
  * here, so this oracle is pinned against independent implementations available in this container
- * (TVM topi `correlation_nchw_python`, torchvision `deform_conv2d` in the interior,
- * torch `grid_sample(align_corners=True)`, torch `conv_transpose2d` for Upsample) -- see
- * tests/golden/make_golden.py and DESIGN.md.  Against MXNet itself: "parity unpinned".
+ * (TVM topi `correlation_nchw_python`, torchvision `deform_conv2d` in the interior and in
+ * zero-corner mode, TVM topi `deformable_conv2d_nchw_python` for the lower half of the MXNet-1.5
+ * border rule (taps in (-1,0) contribute zero), torch `grid_sample(align_corners=True)`, torch
+ * `conv_transpose2d` for Upsample) -- see tests/golden/make_golden*.py and DESIGN.md.
+ * Against MXNet itself: "parity unpinned".
  *
  * Build: see oracle/Makefile (gcc -O2 [-fopenmp]).  All tensors are fp32, NCHW, contiguous.
  */
