@@ -9,6 +9,11 @@ bilinear read), (b) a tap in (n-1, n) collapses on the last pixel.  TVM's refere
 im2col test (`if y < 0 or ...: continue`) and differs from MXNet in (b); on inputs that exercise only (a) it is an
 independent pin of that half of the rule (torchvision pins the zero-corner mode and the interior).
 
+Also written: affine_sampler_tvm.npz -- TVM's `affine_grid_python` (the operator TVM ported from MXNet's
+GridGenerator('affine')) and `grid_sample_2d(bilinear, zeros, align_corners=True)` (= MXNet BilinearSampler semantics) on seeded
+inputs with a grid that partly leaves the image: independent pins of oracle/augment_ref.grid_generator_affine and of the C
+oracle's sampler outside the 'warp' use (row N4's operators).
+
 Run from the repo root (needs only numpy):  python tests/golden/make_golden_deform_tvm.py
 """
 import importlib.util
@@ -62,6 +67,23 @@ def main():
     assert np.abs(mx15 - out).max() < 2e-5 and np.abs(zc - out).max() > 1e-2 and band > 100
     np.savez_compressed(os.path.join(HERE, "deform_tvm_lowband.npz"), x=x, w=w, off=off, out=out)
     print("wrote", os.path.join(HERE, "deform_tvm_lowband.npz"))
+    # ---- GridGenerator('affine') + BilinearSampler against TVM's affine_grid_python / grid_sample_2d ----
+    from oracle import augment_ref
+    spec = importlib.util.spec_from_file_location("_tvm_grid_sample_python", os.path.join(os.path.dirname(TVM_DEFORM), "grid_sample_python.py"))
+    gs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gs)
+    TH, TW = 11, 13
+    theta = np.array([[0.9, 0.2, 0.05, -0.15, 1.1, -0.1], [1.3, -0.4, 0.3, 0.35, 0.8, 0.2], [1, 0, 0, 0, 1, 0]], np.float32)
+    data = rng.standard_normal((3, 4, 9, 10)).astype(np.float32)
+    grid = gs.affine_grid_python(theta.astype(np.float64).reshape(3, 2, 3), (TH, TW)).astype(np.float32)
+    sampled = gs.grid_sample_2d(data.astype(np.float64), grid.astype(np.float64), "bilinear", "NCHW", "zeros", True).astype(np.float32)
+    ours_grid = augment_ref.grid_generator_affine(theta, TH, TW)
+    ours = cref.bilinear_sampler(data, ours_grid)
+    print("affine grid max |oracle - TVM| =", np.abs(ours_grid - grid).max(), " sampler max |oracle - TVM| =", np.abs(ours - sampled).max(),
+          " fraction of grid points outside [-1,1]:", float((np.abs(grid) > 1).any(axis=1).mean()))
+    assert np.abs(ours_grid - grid).max() < 1e-6 and np.abs(ours - sampled).max() < 2e-5 and (np.abs(grid) > 1).any()
+    np.savez_compressed(os.path.join(HERE, "affine_sampler_tvm.npz"), theta=theta, data=data, grid=grid, sampled=sampled)
+    print("wrote", os.path.join(HERE, "affine_sampler_tvm.npz"))
 
 
 if __name__ == "__main__":

@@ -83,6 +83,16 @@ def test_deformable_lower_band_matches_tvm_reference():
     assert np.abs(t - d["out"]).max() < 2e-5                                    # the differentiable restatement too
 
 
+def test_affine_grid_and_sampler_match_tvm_reference():
+    """GridGenerator('affine') (oracle/augment_ref.py, MXNet-recalled) and BilinearSampler (C oracle) against TVM's
+    affine_grid_python / grid_sample_2d(bilinear, zeros, align_corners) -- 19 % of the grid points lie outside the image."""
+    from oracle import augment_ref
+    d = np.load(os.path.join(G, "affine_sampler_tvm.npz"))
+    grid = augment_ref.grid_generator_affine(d["theta"], *d["grid"].shape[2:])
+    assert np.abs(grid - d["grid"]).max() < 1e-6
+    assert np.abs(cref.bilinear_sampler(d["data"], grid) - d["sampled"]).max() < 2e-5
+
+
 def test_deformable_border_rule_mxnet15():
     """The MXNet-1.5 rule on a 1-channel ramp with a centre-tap delta kernel: zero for coordinate < 0, last pixel (no
     blend) for H-1 < h < H, zero for h >= H."""
