@@ -107,11 +107,12 @@ def _color_stub(a, b):
     return a, b
 
 
-def _make_pipeline():
+def _make_pipeline(setattr_=setattr):
+    """setattr_: plain setattr in the spawned workers (their process ends with the test), monkeypatch.setattr in the parent."""
     from maskflownet_b200 import network, ops, pipeline
     from oracle import torch_ref
-    network.MaskFlownetS = _TinyNet
-    ops.upsample = lambda x, f, scale=1.0: torch_ref.upsample(x, f) * scale
+    setattr_(network, "MaskFlownetS", _TinyNet)
+    setattr_(ops, "upsample", lambda x, f, scale=1.0: torch_ref.upsample(x, f) * scale)
     torch.manual_seed(0)
     return pipeline.PipelineFlownet(device="cpu")
 
@@ -137,7 +138,7 @@ def _pipeline_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_gloo_pipeline_train_batch_two_ranks_match_single_process():
+def test_gloo_pipeline_train_batch_two_ranks_match_single_process(monkeypatch):
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -148,7 +149,7 @@ def test_gloo_pipeline_train_batch_two_ranks_match_single_process():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    pipe = _make_pipeline()
+    pipe = _make_pipeline(monkeypatch.setattr)
     img1, img2, label = _train_data()
     for _ in range(2):
         pipe.train_batch(img1, img2, label, _geo_stub, _color_stub)
