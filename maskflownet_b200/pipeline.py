@@ -8,7 +8,7 @@ drives -- same method names, argument meaning and return values -- composed from
     do_batch      pipeline.py:134-147  Upsample(4), resize back + per-channel rescale, Reconstruction2DSmooth, masked EPE
     validate      pipeline.py:149-187  dataset loop -> mean EPE, or the KITTI outlier ratio (return_type != 'epe')
     predict       pipeline.py:189-223  dataset loop -> (flow (H,W,2) in (x,y), occlusion mask, warped image) per sample
-    set_learning_rate / lr / save / load / fix_head    pipeline.py:52-79
+    set_learning_rate / lr / save / load / load_head / fix_head    pipeline.py:52-79
 
 One process drives ONE GPU (the reference splits a batch over a context list inside the process; here the launcher starts
 one rank per GPU and `train_batch` receives this rank's shard -- dist.shard_batch -- the all-reduce does the rest).
@@ -71,8 +71,19 @@ class PipelineFlownet:
         else:
             self.network.load_state_dict(torch.load(checkpoint, map_location=self.device))
 
+    def load_head(self, checkpoint: str) -> None:
+        """Load a MaskFlownet-S checkpoint into the cascade's head (pipeline.py:59-60 -> MaskFlownet.load_head,
+        network/MaskFlownet.py:409-410)."""
+        head = getattr(self.network, "MaskFlownet_S", None)
+        if head is None:
+            raise MaskflowError("load_head: the network has no MaskFlownet_S head (only the cascade does)")
+        if checkpoint.endswith(".params"):
+            mparams.load_checkpoint(head, checkpoint)
+        else:
+            head.load_state_dict(torch.load(checkpoint, map_location=self.device))
+
     def fix_head(self) -> None:
-        """Freeze the MaskFlownet-S head of the cascade (MaskFlownet.fix_head, network/MaskFlownet.py:409-413)."""
+        """Freeze the MaskFlownet-S head of the cascade (MaskFlownet.fix_head, network/MaskFlownet.py:412-414)."""
         head = getattr(self.network, "MaskFlownet_S", None)
         if head is None:
             raise MaskflowError("fix_head: the network has no MaskFlownet_S head (only the cascade does)")

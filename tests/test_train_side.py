@@ -546,6 +546,26 @@ def test_pipeline_host_plumbing_on_cpu(monkeypatch):
         pipe.fix_head()                      # only the cascade has a head to freeze
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/weights/dbbSep30-1206_1000000.params"), reason="shipped checkpoints not on this box")
+def test_pipeline_load_head_and_fix_head_on_cpu():
+    """main.py:133-139: a MaskFlownet-S checkpoint goes into the cascade's head (load_head), which is then frozen (fix_head);
+    the trainer only keeps the cascade's own parameters."""
+    from maskflownet_b200 import params as mparams, pipeline
+    ck = "/root/reference/weights/dbbSep30-1206_1000000.params"
+    pipe = pipeline.PipelineFlownet(device="cpu", network_class="MaskFlownet")
+    pipe.load_head(ck)
+    raw = mparams.read_params(ck)
+    name = next(k for k in raw if k.endswith("conv3bweight"))
+    assert np.array_equal(pipe.network.MaskFlownet_S.conv3b.weight.detach().numpy(), raw[name])
+    n_all = sum(p.numel() for p in pipe.network.parameters())
+    pipe.fix_head()
+    n_train = sum(p.numel() for g in pipe.trainer.param_groups for p in g["params"])
+    assert n_all == 20_655_716 and n_all - n_train == 10_514_256          # the S head's parameters are out of the optimizer
+    assert all(not p.requires_grad for p in pipe.network.MaskFlownet_S.parameters())
+    with pytest.raises(Exception):
+        pipeline.PipelineFlownet(device="cpu").load_head(ck)               # MaskFlownet_S alone has no head to load
+
+
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="first run on hardware happens at round end: the round's GPU allowance was spent before "
                                         "pipeline.py was written (host plumbing is covered by the CPU test above)")
