@@ -365,6 +365,35 @@ def test_kernel_source_multiscale_epe_on_host(emu_loss, q):
         assert np.isfinite(g).all() and np.abs(g - w).max() < 1e-5 * max(1e-3, np.abs(w).max())
 
 
+def test_multiscale_epe_autograd_function_on_host_emulation(emu_loss, monkeypatch):
+    """losses.multiscale_epe's autograd Function (argument marshalling, saved tensors, order / count of the returned gradients,
+    once_differentiable) end to end on CPU tensors: the two C-ABI calls are routed to the host build of the same kernels."""
+    from maskflownet_b200 import losses, ops
+
+    def fake_call(name, dev, *args):
+        conv = [ctypes.c_float(a) if isinstance(a, float) else a for a in args]
+        if name == "mfn_multiscale_epe_forward":       # (..., loss, mask_sum, workspace, workspace_bytes, N, H, W)
+            emu_loss.emu_epe_forward(*conv[:10], *conv[12:15])
+        elif name == "mfn_multiscale_epe_backward":
+            emu_loss.emu_epe_backward(*conv)
+        else:
+            raise AssertionError(name)
+    monkeypatch.setattr(ops, "_call", fake_call)
+    monkeypatch.setattr(ops, "_chk", lambda t, name, optional=False: t if t is None else t.contiguous())
+    scales, weights = (16, 8, 4), (.02, .08, .32)
+    N, H, W = 2, 32, 48
+    preds, flow, mask, gl = epe_case(11, N, H, W, scales)
+    want_loss, want_grads = epe_oracle(preds, flow, mask, gl, scales, weights, 1e-8, None)
+    tp = [torch.from_numpy(p).clone().requires_grad_() for p in preds]
+    loss = losses.multiscale_epe(torch.from_numpy(flow), torch.from_numpy(mask), tp, scales=scales, weights=weights, fused=True)
+    assert np.abs(loss.detach().numpy() - want_loss).max() < 1e-5 * max(1.0, np.abs(want_loss).max())
+    (loss * torch.from_numpy(gl)).sum().backward()
+    for t, w in zip(tp, want_grads):
+        assert t.grad is not None and np.abs(t.grad.numpy() - w).max() < 1e-5 * max(1e-3, np.abs(w).max())
+    with pytest.raises(Exception):                       # the label is data: no gradient is defined for it
+        losses.multiscale_epe(torch.from_numpy(flow).requires_grad_(), torch.from_numpy(mask), tp, scales=scales, weights=weights, fused=True)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("q,N,H,W", [(None, 2, 64, 128), (0.4, 3, 128, 192), (None, 8, 384, 512)])
 def test_multiscale_epe_fused_parity(q, N, H, W):
