@@ -119,7 +119,8 @@ class PipelineFlownet:
     def train_batch(self, img1, img2, label, geo_aug, color_aug, mask=None, global_batch: Optional[int] = None) -> Dict[str, float]:
         """One optimisation step on this rank's shard.  img1 / img2 (n,3,H,W) uint8, label (n,2,H,W) flow in (x,y) pixel
         order (flipped to the network's (y,x) after the augmentation, pipeline.py:106), mask (n,1,H,W) uint8 or None.
-        global_batch: the batch size over ALL ranks (default: n * world size) -- what Trainer.step(batch_size) divides by."""
+        global_batch: the batch size over ALL ranks (default: n * world size) -- what Trainer.step(batch_size) divides by.
+        Returns {"epe": mean EPE of THIS rank's samples} (the reference averages over its context list in one process)."""
         dev = self.device
         n = img1.shape[0]
         if mask is None:
